@@ -1,0 +1,821 @@
+// rtb200_host.cu — host layer of librtb200.so: context (stream, pinned staging, device arena),
+// problem staging, chunked launch of the march / integration kernels, and the extern "C" ABI
+// declared in include/rtb200.h.  C++ in the reference's own style; no CPU fallback: every
+// compute entry point fails with RTB200_ERR_CUDA when the device is not usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rtb200.h"
+#include "rtb200_kernels.cuh"
+#include "rtb200_pack.h"
+
+using namespace rtb;
+
+#define RTB_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                     \
+            return RTB200_ERR_CUDA;                                                            \
+        }                                                                                      \
+    } while (0)
+
+namespace {
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0; // elements
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap)
+            return cudaSuccess;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMalloc((void **) &p, want * sizeof(T));
+        if (e == cudaSuccess)
+            cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinBuf {
+    char *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap)
+            return cudaSuccess;
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = n + n / 4 + 4096;
+        cudaError_t e = cudaMallocHost((void **) &p, want);
+        if (e == cudaSuccess)
+            cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+} // namespace
+
+struct rtb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // staging
+    PinBuf h_blob;
+    DevBuf<char> d_blob;
+    DevProblem prob;
+    bool staged = false;
+    bool owner_ok = false; // ASE owner kernel usable (identity-like, injective pixel map)
+    long long staged_pixels = 0, staged_rays = 0;
+    // hand-off
+    DevBuf<SegRec> d_seg;
+    DevBuf<unsigned> d_meta;
+    DevBuf<float4> d_exit;
+    long long slots_per_chunk = 0;
+    // outputs for the host-buffer API
+    DevBuf<double> d_image, d_iang, d_Iv;
+    DevBuf<int> d_err;
+    DevBuf<float4> d_rays;
+    DevBuf<float2> d_tans;
+    PinBuf h_out;
+    FailState *d_fail = nullptr;
+    FailState *h_fail = nullptr; // pinned
+    // timing
+    std::vector<cudaEvent_t> ev;
+    size_t ev_used = 0;
+    std::vector<std::pair<size_t, size_t>> ev_march, ev_integ; // (start, stop) indices
+    std::pair<size_t, size_t> ev_h2d{ 0, 0 }, ev_d2h{ 0, 0 };
+    bool have_h2d = false, have_d2h = false;
+    rtb200_timings last;
+    int launches = 0;
+    bool count_steps = false;
+    size_t handoff_bytes = 256u << 20;
+};
+
+namespace {
+
+size_t new_event(rtb200_ctx *ctx, cudaStream_t st)
+{
+    if (ctx->ev_used == ctx->ev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->ev.push_back(e);
+    }
+    cudaEventRecord(ctx->ev[ctx->ev_used], st);
+    return ctx->ev_used++;
+}
+
+void reset_timing(rtb200_ctx *ctx)
+{
+    ctx->ev_used = 0;
+    ctx->ev_march.clear();
+    ctx->ev_integ.clear();
+    ctx->have_h2d = ctx->have_d2h = false;
+    ctx->launches = 0;
+}
+
+float ev_ms(rtb200_ctx *ctx, std::pair<size_t, size_t> p)
+{
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[p.first], ctx->ev[p.second]);
+    return ms;
+}
+
+void collect_timing(rtb200_ctx *ctx)
+{
+    rtb200_timings &t = ctx->last;
+    std::memset(&t, 0, sizeof(t));
+    if (ctx->have_h2d)
+        t.h2d_ms = ev_ms(ctx, ctx->ev_h2d);
+    if (ctx->have_d2h)
+        t.d2h_ms = ev_ms(ctx, ctx->ev_d2h);
+    for (auto &p : ctx->ev_march)
+        t.march_ms += ev_ms(ctx, p);
+    for (auto &p : ctx->ev_integ)
+        t.integrate_ms += ev_ms(ctx, p);
+    if (ctx->ev_used >= 2)
+        t.total_ms = ev_ms(ctx, { 0, ctx->ev_used - 1 });
+    t.kernel_launches = ctx->launches;
+    t.n_rays = (uint64_t) ctx->staged_rays;
+    t.march_steps = ctx->h_fail ? ctx->h_fail->march_steps : 0;
+}
+
+// check_grid (src/RayTraceImage.cpp:237-242)
+bool grid_error(int n, double dx, const double *x)
+{
+    bool error = false;
+    for (int i = 1; i < n; i++)
+        error = error || (std::fabs((x[i] - x[i - 1]) - dx) > 1e-12 * dx);
+    return error;
+}
+
+int validate(rtb200_ctx *ctx, const rtb200_problem *p, unsigned flags)
+{
+    if (!p || !p->euv_beam || !p->gain || p->N < 1 || p->N_parallel < 1 || p->N_start < 0) {
+        ctx->err = "invalid problem (NULL member, N < 1, N_parallel < 1 or N_start < 0)";
+        return RTB200_ERR_ARG;
+    }
+    if (p->seed && !p->seed_beam) {
+        ctx->err = "seed given without seed_beam";
+        return RTB200_ERR_ARG;
+    }
+    const rtb200_beam &e = *p->euv_beam;
+    if (!(flags & RTB200_FLAG_NO_LIMITS)) { // src/RayTraceImage.cpp:229-232
+        if (p->N > RTB200_N_MAX) {
+            ctx->err = "Exceeded maximum number of length segments";
+            return RTB200_ERR_LIMITS;
+        }
+        if (e.nv >= RTB200_K_MAX) {
+            ctx->err = "Exceeded maximum number of frequencies";
+            return RTB200_ERR_LIMITS;
+        }
+    }
+    if ((p->N - 1) * RTB200_N_SUB > RTB_MAX_SEGS) {
+        ctx->err = "too many length segments for the hand-off record";
+        return RTB200_ERR_LIMITS;
+    }
+    if (grid_error(e.nx, e.dx, e.x) || grid_error(e.ny, e.dy, e.y) ||
+        grid_error(e.na, e.da, e.a) || grid_error(e.nb, e.db, e.b)) { // :243-250
+        ctx->err = "Only uniform grid spacings are currently supported (euv_beam)";
+        return RTB200_ERR_GRID;
+    }
+    if (p->seed_beam) { // :253-264
+        const rtb200_beam &s = *p->seed_beam;
+        if (grid_error(s.nx, s.dx, s.x) || grid_error(s.ny, s.dy, s.y) ||
+            grid_error(s.na, s.da, s.a) || grid_error(s.nb, s.db, s.b)) {
+            ctx->err = "Only uniform grid spacings are currently supported (seed_beam)";
+            return RTB200_ERR_GRID;
+        }
+        if ((e.y[0] >= 0.0) != (s.y[0] >= 0.0)) {
+            ctx->err = "Negitive y positions in seed_beam or euv_beam, but not both";
+            return RTB200_ERR_GRID;
+        }
+    }
+    for (int i = 0; i < p->N; i++) {
+        const rtb200_gain_plane &g = p->gain[i];
+        if (g.Nx < 2 || g.Ny < 2 || g.Nv != e.nv || !g.x || !g.y || !g.n || !g.g0 || !g.gv) {
+            ctx->err = "invalid gain plane (Nx, Ny < 2, Nv != nv or NULL array)";
+            return RTB200_ERR_ARG;
+        }
+    }
+    return RTB200_OK;
+}
+
+bool injective(const int *t, int n, int range)
+{
+    std::vector<char> seen((size_t) std::max(range, 1), 0);
+    for (int i = 0; i < n; i++) {
+        if (t[i] < 0)
+            continue;
+        if (t[i] >= range || seen[t[i]])
+            return false;
+        seen[t[i]] = 1;
+    }
+    return true;
+}
+
+int stage_impl(rtb200_ctx *ctx, const rtb200_problem *p, bool explicit_rays, int method,
+               double scale)
+{
+    RTB_CUDA(cudaSetDevice(ctx->device));
+    DevProblem tmp;
+    const size_t bytes = pack_problem(*p, explicit_rays, method, scale, nullptr, nullptr, tmp);
+    RTB_CUDA(ctx->h_blob.reserve(bytes));
+    RTB_CUDA(ctx->d_blob.reserve(bytes));
+    pack_problem(*p, explicit_rays, method, scale, ctx->h_blob.p, ctx->d_blob.p, ctx->prob);
+    ctx->ev_h2d.first = new_event(ctx, ctx->stream);
+    RTB_CUDA(cudaMemsetAsync(ctx->d_fail, 0, sizeof(FailState), ctx->stream));
+    RTB_CUDA(cudaMemcpyAsync(ctx->d_blob.p, ctx->h_blob.p, bytes, cudaMemcpyHostToDevice,
+                             ctx->stream));
+    ctx->ev_h2d.second = new_event(ctx, ctx->stream);
+    ctx->have_h2d = true;
+    ctx->staged = true;
+    const DevProblem &P = ctx->prob;
+    if (!explicit_rays) {
+        ctx->staged_pixels = (long long) P.snx * P.sny;
+        const long long Nt = ctx->staged_pixels * P.sna * P.snb;
+        ctx->staged_rays = P.n_start < Nt ? (Nt - P.n_start + P.n_parallel - 1) / P.n_parallel : 0;
+        // The owner kernel needs each destination pixel to be fed by at most one source pixel.
+        const char *hb = ctx->h_blob.p;
+        const char *db = ctx->d_blob.p;
+        const int *pixI = reinterpret_cast<const int *>(hb + ((const char *) P.pixI - db));
+        const int *pixJ = reinterpret_cast<const int *>(hb + ((const char *) P.pixJ - db));
+        ctx->owner_ok = P.method == 1 && P.use_emis && injective(pixI, P.snx, P.nx) &&
+                        injective(pixJ, P.sny, P.ny);
+    } else {
+        ctx->staged_pixels = 0;
+        ctx->staged_rays = 0;
+        ctx->owner_ok = false;
+    }
+    return RTB200_OK;
+}
+
+int ensure_handoff(rtb200_ctx *ctx, long long slots, bool need_exit)
+{
+    const int S = (ctx->prob.N - 1) * RTB_N_SUB;
+    RTB_CUDA(ctx->d_seg.reserve((size_t) slots * (size_t) std::max(S, 1)));
+    RTB_CUDA(ctx->d_meta.reserve((size_t) slots));
+    if (need_exit)
+        RTB_CUDA(ctx->d_exit.reserve((size_t) slots));
+    return RTB200_OK;
+}
+
+// Launches the kernels for source pixels [pix0, pix1) in chunks whose hand-off fits the budget.
+int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs &out,
+                  cudaStream_t st)
+{
+    const DevProblem &P = ctx->prob;
+    if (pix1 <= pix0)
+        return RTB200_OK;
+    const int S = (P.N - 1) * RTB_N_SUB;
+    const bool need_exit = P.method != 1;
+    const size_t per_slot = (size_t) std::max(S, 1) * sizeof(SegRec) + sizeof(unsigned) +
+                            (need_exit ? sizeof(float4) : 0);
+    long long pix_per_chunk =
+        std::max<long long>(1, (long long) (ctx->handoff_bytes / per_slot) / std::max(P.ab_max, 1));
+    pix_per_chunk = std::min(pix_per_chunk, pix1 - pix0);
+    int rc = ensure_handoff(ctx, pix_per_chunk * P.ab_max, need_exit);
+    if (rc)
+        return rc;
+    Handoff h{ ctx->d_seg.p, ctx->d_meta.p, need_exit ? ctx->d_exit.p : nullptr };
+    for (long long a = pix0; a < pix1; a += pix_per_chunk) {
+        Chunk c;
+        std::memset(&c, 0, sizeof(c));
+        c.pix0 = a;
+        c.pix1 = std::min(pix1, a + pix_per_chunk);
+        const size_t e0 = new_event(ctx, st);
+        launch_march(P, c, false, h, ctx->d_fail, ctx->count_steps, st);
+        const size_t e1 = new_event(ctx, st);
+        if (ctx->owner_ok && !out.Iv && !out.error)
+            launch_integrate_ase_owner(P, c, h, out, st);
+        else
+            launch_integrate_scatter(P, c, false, h, out, st);
+        const size_t e2 = new_event(ctx, st);
+        ctx->ev_march.push_back({ e0, e1 });
+        ctx->ev_integ.push_back({ e1, e2 });
+        ctx->launches += 2;
+    }
+    RTB_CUDA(cudaGetLastError());
+    return RTB200_OK;
+}
+
+int finish(rtb200_ctx *ctx, unsigned *failure_code, rtb200_ray *failed, int max_failed,
+           int *n_failed)
+{
+    RTB_CUDA(cudaMemcpyAsync(ctx->h_fail, ctx->d_fail, sizeof(FailState), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    RTB_CUDA(cudaMemsetAsync(ctx->d_fail, 0, sizeof(FailState), ctx->stream));
+    new_event(ctx, ctx->stream);
+    RTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    collect_timing(ctx);
+    const FailState &f = *ctx->h_fail;
+    if (failure_code)
+        *failure_code = f.failure_code;
+    if (n_failed)
+        *n_failed = (int) f.n_failed;
+    if (failed) {
+        const int n = std::min<int>({ (int) f.n_failed, max_failed, 32 });
+        for (int i = 0; i < n; i++) {
+            failed[i].x = f.failed[4 * i + 0];
+            failed[i].y = f.failed[4 * i + 1];
+            failed[i].a = f.failed[4 * i + 2];
+            failed[i].b = f.failed[4 * i + 3];
+        }
+    }
+    return f.failure_code ? RTB200_RAYS_FAILED : RTB200_OK;
+}
+
+} // namespace
+
+// =============================================================================================
+// extern "C" ABI
+// =============================================================================================
+extern "C" {
+
+const char *rtb200_version(void) { return "rtb200 0.1.0 (sm_100a)"; }
+
+int rtb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int rtb200_create(int device, rtb200_ctx **out)
+{
+    if (!out)
+        return RTB200_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+        cudaGetLastError();
+        return RTB200_ERR_CUDA;
+    }
+    rtb200_ctx *ctx = new rtb200_ctx;
+    ctx->device = device;
+    std::memset(&ctx->last, 0, sizeof(ctx->last));
+    std::memset(&ctx->prob, 0, sizeof(ctx->prob));
+    auto fail = [&](cudaError_t e) {
+        (void) e;
+        cudaGetLastError();
+        delete ctx;
+        return RTB200_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess)
+        return fail(e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return fail(e);
+    if ((e = cudaMalloc((void **) &ctx->d_fail, sizeof(FailState))) != cudaSuccess)
+        return fail(e);
+    if ((e = cudaMallocHost((void **) &ctx->h_fail, sizeof(FailState))) != cudaSuccess)
+        return fail(e);
+    std::memset(ctx->h_fail, 0, sizeof(FailState));
+    if (const char *s = getenv("RTB200_HANDOFF_MB"))
+        ctx->handoff_bytes = (size_t) std::max(1, atoi(s)) << 20;
+    if (const char *s = getenv("RTB200_COUNT_STEPS"))
+        ctx->count_steps = atoi(s) != 0;
+    *out = ctx;
+    return RTB200_OK;
+}
+
+void rtb200_destroy(rtb200_ctx *ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream)
+        cudaStreamSynchronize(ctx->stream);
+    ctx->h_blob.release();
+    ctx->d_blob.release();
+    ctx->d_seg.release();
+    ctx->d_meta.release();
+    ctx->d_exit.release();
+    ctx->d_image.release();
+    ctx->d_iang.release();
+    ctx->d_Iv.release();
+    ctx->d_err.release();
+    ctx->d_rays.release();
+    ctx->d_tans.release();
+    ctx->h_out.release();
+    if (ctx->d_fail)
+        cudaFree(ctx->d_fail);
+    if (ctx->h_fail)
+        cudaFreeHost(ctx->h_fail);
+    for (auto e : ctx->ev)
+        cudaEventDestroy(e);
+    if (ctx->stream)
+        cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *rtb200_last_error(const rtb200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int rtb200_stage(rtb200_ctx *ctx, const rtb200_problem *problem, unsigned flags)
+{
+    if (!ctx)
+        return RTB200_ERR_ARG;
+    int rc = validate(ctx, problem, flags);
+    if (rc)
+        return rc;
+    reset_timing(ctx);
+    new_event(ctx, ctx->stream);
+    return stage_impl(ctx, problem, false, 0, 0.0);
+}
+
+int64_t rtb200_staged_pixels(const rtb200_ctx *ctx) { return ctx && ctx->staged ? ctx->staged_pixels : 0; }
+int64_t rtb200_staged_rays(const rtb200_ctx *ctx) { return ctx && ctx->staged ? ctx->staged_rays : 0; }
+
+int rtb200_launch(rtb200_ctx *ctx, int64_t pix_begin, int64_t pix_end, double *d_image,
+                  double *d_I_ang, void *cuda_stream)
+{
+    if (!ctx || !ctx->staged || !d_image || !d_I_ang || pix_begin < 0 ||
+        pix_end > ctx->staged_pixels) {
+        if (ctx)
+            ctx->err = "rtb200_launch: nothing staged or bad argument";
+        return RTB200_ERR_ARG;
+    }
+    RTB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : ctx->stream;
+    if (st != ctx->stream) { // order after the staging upload
+        cudaEvent_t e;
+        RTB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        RTB_CUDA(cudaEventRecord(e, ctx->stream));
+        RTB_CUDA(cudaStreamWaitEvent(st, e, 0));
+        RTB_CUDA(cudaEventDestroy(e));
+    }
+    if (ctx->ev_used > 64 + 3 * 4096) // a long series of launches on one staging: keep the pool bounded
+        reset_timing(ctx);
+    Outputs out{ d_image, d_I_ang, nullptr, nullptr, ctx->d_fail };
+    return launch_pixels(ctx, pix_begin, pix_end, out, st);
+}
+
+int rtb200_sync(rtb200_ctx *ctx, unsigned *failure_code, rtb200_ray *failed, int max_failed,
+                int *n_failed)
+{
+    if (!ctx)
+        return RTB200_ERR_ARG;
+    RTB_CUDA(cudaSetDevice(ctx->device));
+    RTB_CUDA(cudaDeviceSynchronize());
+    return finish(ctx, failure_code, failed, max_failed, n_failed);
+}
+
+int rtb200_get_timings(const rtb200_ctx *ctx, rtb200_timings *out)
+{
+    if (!ctx || !out)
+        return RTB200_ERR_ARG;
+    *out = ctx->last;
+    return RTB200_OK;
+}
+
+int rtb200_create_image(rtb200_ctx *ctx, const rtb200_problem *problem, unsigned flags,
+                        double *image, double *I_ang, unsigned *failure_code,
+                        rtb200_ray *failed, int max_failed, int *n_failed)
+{
+    if (!ctx || !image || !I_ang) {
+        if (ctx)
+            ctx->err = "rtb200_create_image: NULL argument";
+        return RTB200_ERR_ARG;
+    }
+    int rc = validate(ctx, problem, flags);
+    if (rc)
+        return rc;
+    reset_timing(ctx);
+    new_event(ctx, ctx->stream);
+    rc = stage_impl(ctx, problem, false, 0, 0.0);
+    if (rc)
+        return rc;
+    const DevProblem &P = ctx->prob;
+    const size_t n_img = (size_t) P.nx * P.ny * P.K, n_ang = (size_t) P.na * P.nb;
+    RTB_CUDA(ctx->d_image.reserve(n_img));
+    RTB_CUDA(ctx->d_iang.reserve(n_ang));
+    RTB_CUDA(cudaMemsetAsync(ctx->d_image.p, 0, n_img * sizeof(double), ctx->stream));
+    RTB_CUDA(cudaMemsetAsync(ctx->d_iang.p, 0, n_ang * sizeof(double), ctx->stream));
+    Outputs out{ ctx->d_image.p, ctx->d_iang.p, nullptr, nullptr, ctx->d_fail };
+    rc = launch_pixels(ctx, 0, ctx->staged_pixels, out, ctx->stream);
+    if (rc)
+        return rc;
+    ctx->ev_d2h.first = new_event(ctx, ctx->stream);
+    RTB_CUDA(cudaMemcpyAsync(image, ctx->d_image.p, n_img * sizeof(double), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    RTB_CUDA(cudaMemcpyAsync(I_ang, ctx->d_iang.p, n_ang * sizeof(double), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    ctx->ev_d2h.second = new_event(ctx, ctx->stream);
+    ctx->have_d2h = true;
+    return finish(ctx, failure_code, failed, max_failed, n_failed);
+}
+
+namespace {
+
+// tanf(1e-3f*a) per ray through a small open-addressing cache keyed by the float's bits: ray
+// lists enumerate a grid, so only na + nb distinct angles occur.
+struct TanCache {
+    static const int CAP = 8192;
+    uint32_t key[CAP];
+    float val[CAP];
+    bool used[CAP];
+    int count = 0;
+    TanCache() { std::memset(used, 0, sizeof(used)); }
+    float get(float a)
+    {
+        uint32_t bits;
+        std::memcpy(&bits, &a, 4);
+        uint32_t h = (bits * 2654435761u) >> 19; // 13 bits
+        for (int probe = 0; probe < 16; probe++) {
+            const uint32_t s = (h + probe) & (CAP - 1);
+            if (used[s] && key[s] == bits)
+                return val[s];
+            if (!used[s]) {
+                if (count > CAP / 2)
+                    break;
+                used[s] = true;
+                key[s] = bits;
+                val[s] = tanf(1e-3f * a);
+                count++;
+                return val[s];
+            }
+        }
+        return tanf(1e-3f * a);
+    }
+};
+
+int upload_rays(rtb200_ctx *ctx, const rtb200_ray *rays, size_t n)
+{
+    RTB_CUDA(ctx->d_rays.reserve(n));
+    RTB_CUDA(ctx->d_tans.reserve(n));
+    RTB_CUDA(ctx->h_out.reserve(n * sizeof(float2)));
+    float2 *t = reinterpret_cast<float2 *>(ctx->h_out.p);
+    TanCache cache;
+    for (size_t i = 0; i < n; i++) {
+        t[i].x = cache.get(rays[i].a);
+        t[i].y = cache.get(rays[i].b);
+    }
+    RTB_CUDA(cudaMemcpyAsync(ctx->d_rays.p, rays, n * sizeof(float4), cudaMemcpyHostToDevice,
+                             ctx->stream));
+    RTB_CUDA(cudaMemcpyAsync(ctx->d_tans.p, t, n * sizeof(float2), cudaMemcpyHostToDevice,
+                             ctx->stream));
+    return RTB200_OK;
+}
+
+// Marches + integrates an explicit ray list in chunks.
+int launch_list(rtb200_ctx *ctx, size_t n_rays, const Outputs &out_all, bool keep_handoff)
+{
+    const DevProblem &P = ctx->prob;
+    const int S = (P.N - 1) * RTB_N_SUB;
+    const size_t per_slot = (size_t) std::max(S, 1) * sizeof(SegRec) + sizeof(unsigned) + sizeof(float4);
+    long long per_chunk = keep_handoff ? (long long) n_rays
+                                       : std::max<long long>(1, (long long) (ctx->handoff_bytes / per_slot));
+    per_chunk = std::min<long long>(per_chunk, (long long) n_rays);
+    int rc = ensure_handoff(ctx, per_chunk, true);
+    if (rc)
+        return rc;
+    Handoff h{ ctx->d_seg.p, ctx->d_meta.p, ctx->d_exit.p };
+    for (long long a = 0; a < (long long) n_rays; a += per_chunk) {
+        Chunk c;
+        std::memset(&c, 0, sizeof(c));
+        c.ray0 = a;
+        c.ray1 = std::min<long long>((long long) n_rays, a + per_chunk);
+        c.rays = ctx->d_rays.p;
+        c.tans = ctx->d_tans.p;
+        Outputs out = out_all;
+        if (out.Iv)
+            out.Iv += (size_t) a * P.K;
+        if (out.error)
+            out.error += a;
+        const size_t e0 = new_event(ctx, ctx->stream);
+        launch_march(P, c, true, h, ctx->d_fail, ctx->count_steps, ctx->stream);
+        const size_t e1 = new_event(ctx, ctx->stream);
+        launch_integrate_scatter(P, c, true, h, out, ctx->stream);
+        const size_t e2 = new_event(ctx, ctx->stream);
+        ctx->ev_march.push_back({ e0, e1 });
+        ctx->ev_integ.push_back({ e1, e2 });
+        ctx->launches += 2;
+    }
+    RTB_CUDA(cudaGetLastError());
+    return RTB200_OK;
+}
+
+} // namespace
+
+int rtb200_trace_rays(rtb200_ctx *ctx, int N, const rtb200_beam *beam,
+                      const rtb200_gain_plane *gain, const rtb200_seed *seed, int method,
+                      const rtb200_ray *rays, size_t n_rays, double scale, double *image,
+                      double *I_ang, unsigned *failure_code, rtb200_ray *failed,
+                      int max_failed, int *n_failed)
+{
+    if (!ctx || !beam || !gain || !image || !I_ang || (n_rays && !rays) ||
+        (method != 1 && method != 2)) {
+        if (ctx)
+            ctx->err = "rtb200_trace_rays: bad argument";
+        return RTB200_ERR_ARG;
+    }
+    if (seed) {
+        ctx->err = "rtb200_trace_rays: explicit ray lists with a seed beam are not supported yet "
+                   "(use rtb200_create_image)";
+        return RTB200_ERR_ARG;
+    }
+    rtb200_problem p;
+    std::memset(&p, 0, sizeof(p));
+    p.N = N;
+    p.N_start = 0;
+    p.N_parallel = 1;
+    p.euv_beam = beam;
+    p.gain = gain;
+    p.seed = seed;
+    int rc = validate(ctx, &p, RTB200_FLAG_NO_LIMITS);
+    if (rc)
+        return rc;
+    reset_timing(ctx);
+    new_event(ctx, ctx->stream);
+    rc = stage_impl(ctx, &p, true, method, scale);
+    if (rc)
+        return rc;
+    const DevProblem &P = ctx->prob;
+    const size_t n_img = (size_t) P.nx * P.ny * P.K, n_ang = (size_t) P.na * P.nb;
+    RTB_CUDA(ctx->d_image.reserve(n_img));
+    RTB_CUDA(ctx->d_iang.reserve(n_ang));
+    RTB_CUDA(cudaMemsetAsync(ctx->d_image.p, 0, n_img * sizeof(double), ctx->stream));
+    RTB_CUDA(cudaMemsetAsync(ctx->d_iang.p, 0, n_ang * sizeof(double), ctx->stream));
+    if (n_rays) {
+        rc = upload_rays(ctx, rays, n_rays);
+        if (rc)
+            return rc;
+        Outputs out{ ctx->d_image.p, ctx->d_iang.p, nullptr, nullptr, ctx->d_fail };
+        rc = launch_list(ctx, n_rays, out, false);
+        if (rc)
+            return rc;
+    }
+    // accumulate into the caller's buffers, like the CPU loop (src/RayTraceImageCPU.cpp:56-68)
+    std::vector<double> tmp(n_img + n_ang);
+    ctx->ev_d2h.first = new_event(ctx, ctx->stream);
+    RTB_CUDA(cudaMemcpyAsync(tmp.data(), ctx->d_image.p, n_img * sizeof(double),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    RTB_CUDA(cudaMemcpyAsync(tmp.data() + n_img, ctx->d_iang.p, n_ang * sizeof(double),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->ev_d2h.second = new_event(ctx, ctx->stream);
+    ctx->have_d2h = true;
+    rc = finish(ctx, failure_code, failed, max_failed, n_failed);
+    if (rc < 0)
+        return rc;
+    for (size_t i = 0; i < n_img; i++)
+        image[i] += tmp[i];
+    for (size_t i = 0; i < n_ang; i++)
+        I_ang[i] += tmp[n_img + i];
+    return rc;
+}
+
+int rtb200_calc_rays(rtb200_ctx *ctx, int N, double dz, const rtb200_gain_plane *gain,
+                     const rtb200_seed *seed, int K, int method, const rtb200_ray *rays,
+                     size_t n_rays, double *Iv, rtb200_ray *ray2, int *error, float *gvl,
+                     float *evl, int32_t *ivl)
+{
+    if (!ctx || !gain || (n_rays && !rays) || (method != 1 && method != 2) || K < 1) {
+        if (ctx)
+            ctx->err = "rtb200_calc_rays: bad argument";
+        return RTB200_ERR_ARG;
+    }
+    if (seed) {
+        ctx->err = "rtb200_calc_rays: seed beams are not supported yet";
+        return RTB200_ERR_ARG;
+    }
+    rtb200_beam beam;
+    std::memset(&beam, 0, sizeof(beam));
+    beam.nv = K;
+    beam.dz = dz;
+    rtb200_problem p;
+    std::memset(&p, 0, sizeof(p));
+    p.N = N;
+    p.N_parallel = 1;
+    p.euv_beam = &beam;
+    p.gain = gain;
+    if (N < 1 || (N - 1) * RTB200_N_SUB > RTB_MAX_SEGS) {
+        ctx->err = "rtb200_calc_rays: bad N";
+        return RTB200_ERR_ARG;
+    }
+    for (int i = 0; i < N; i++)
+        if (gain[i].Nx < 2 || gain[i].Ny < 2 || gain[i].Nv != K) {
+            ctx->err = "rtb200_calc_rays: invalid gain plane";
+            return RTB200_ERR_ARG;
+        }
+    reset_timing(ctx);
+    new_event(ctx, ctx->stream);
+    int rc = stage_impl(ctx, &p, true, method, 1.0);
+    if (rc)
+        return rc;
+    if (!n_rays)
+        return RTB200_OK;
+    const int S = (N - 1) * RTB_N_SUB;
+    rc = upload_rays(ctx, rays, n_rays);
+    if (rc)
+        return rc;
+    RTB_CUDA(ctx->d_Iv.reserve(n_rays * (size_t) K));
+    RTB_CUDA(ctx->d_err.reserve(n_rays));
+    Outputs out{ nullptr, nullptr, ctx->d_Iv.p, ctx->d_err.p, ctx->d_fail };
+    rc = launch_list(ctx, n_rays, out, true);
+    if (rc)
+        return rc;
+    std::vector<SegRec> seg((size_t) n_rays * (size_t) std::max(S, 1));
+    std::vector<unsigned> meta(n_rays);
+    std::vector<float4> ex(n_rays);
+    std::vector<int> err(n_rays);
+    if (Iv)
+        RTB_CUDA(cudaMemcpyAsync(Iv, ctx->d_Iv.p, n_rays * (size_t) K * sizeof(double),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    RTB_CUDA(cudaMemcpyAsync(err.data(), ctx->d_err.p, n_rays * sizeof(int), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    if (S > 0)
+        RTB_CUDA(cudaMemcpyAsync(seg.data(), ctx->d_seg.p, n_rays * (size_t) S * sizeof(SegRec),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    RTB_CUDA(cudaMemcpyAsync(meta.data(), ctx->d_meta.p, n_rays * sizeof(unsigned),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    RTB_CUDA(cudaMemcpyAsync(ex.data(), ctx->d_exit.p, n_rays * sizeof(float4),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    rc = finish(ctx, nullptr, nullptr, 0, nullptr);
+    if (rc < 0)
+        return rc;
+    for (size_t r = 0; r < n_rays; r++) {
+        const int lo = meta[r] & 0xfff, hi = (meta[r] >> 12) & 0xfff;
+        for (int s = 0; s < S; s++) {
+            const bool in = s >= lo && s < hi;
+            const SegRec &q = seg[r * (size_t) S + s];
+            if (gvl)
+                gvl[r * (size_t) S + s] = in ? q.gvl : 0.0f;
+            if (evl)
+                evl[r * (size_t) S + s] = in ? q.evl : 0.0f;
+            if (ivl)
+                ivl[r * (size_t) S + s] = in ? q.cell : 0;
+        }
+        if (error)
+            error[r] = err[r];
+        if (ray2) {
+            const bool invalid = (meta[r] & RTB_META_INVALID) != 0;
+            ray2[r].x = invalid ? 0.0f : ex[r].x;
+            ray2[r].y = invalid ? 0.0f : ex[r].y;
+            ray2[r].a = invalid ? 0.0f : ex[r].z;
+            ray2[r].b = invalid ? 0.0f : ex[r].w;
+        }
+    }
+    return RTB200_OK;
+}
+
+int rtb200_measure_fp64_peak(rtb200_ctx *ctx, double *rate)
+{
+    if (!ctx || !rate)
+        return RTB200_ERR_ARG;
+    RTB_CUDA(cudaSetDevice(ctx->device));
+    RTB_CUDA(ctx->d_Iv.reserve(16));
+    int blocks = 0, threads = 0;
+    const int iters = 4096;
+    launch_fp64_peak(ctx->d_Iv.p, 64, ctx->stream, &blocks, &threads); // warm-up
+    cudaEvent_t a, b;
+    RTB_CUDA(cudaEventCreate(&a));
+    RTB_CUDA(cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        RTB_CUDA(cudaEventRecord(a, ctx->stream));
+        launch_fp64_peak(ctx->d_Iv.p, iters, ctx->stream, &blocks, &threads);
+        RTB_CUDA(cudaEventRecord(b, ctx->stream));
+        RTB_CUDA(cudaEventSynchronize(b));
+        float ms = 0;
+        RTB_CUDA(cudaEventElapsedTime(&ms, a, b));
+        const double r = (double) blocks * threads * (double) iters * 8.0 / (ms * 1e-3);
+        best = std::max(best, r);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *rate = best;
+    return RTB200_OK;
+}
+
+} // extern "C"

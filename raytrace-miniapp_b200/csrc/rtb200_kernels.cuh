@@ -1,0 +1,46 @@
+// rtb200_kernels.cuh — launch interface between the host layer (rtb200_host.cu) and the
+// sm_100a kernels (rtb200_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "rtb200_device.cuh"
+
+namespace rtb {
+
+// A contiguous range of source pixels [pix0, pix1) in x-fastest order (p = i + j*snx), or, in
+// list mode, a contiguous range of explicit rays.
+struct Chunk {
+    long long pix0, pix1;   // grid mode
+    long long ray0, ray1;   // list mode (explicit rays)
+    const float4 *rays;     // list mode: (x, y, a, b) per ray
+    const float2 *tans;     // list mode: host tanf(1e-3f*a), tanf(1e-3f*b) per ray
+};
+
+struct Handoff {
+    SegRec *seg;        // [slots * S]
+    unsigned *meta;     // [slots]
+    float4 *exit_ray;   // [slots] ray2 = (x, y, a, b) at exit; may be null (ASE binning never reads it)
+};
+
+// Output selection of the integration kernel.
+struct Outputs {
+    double *image;   // [nx*ny*nv]
+    double *I_ang;   // [na*nb]
+    double *Iv;      // per-ray dump [slots*K] (rtb200_calc_rays) or null
+    int *error;      // per-ray error code dump or null
+    FailState *fail; // never null
+};
+
+void launch_march(const DevProblem &P, const Chunk &c, bool list_mode, const Handoff &h,
+                  FailState *fail, bool count_steps, cudaStream_t st);
+// ASE (method 1, emission + gain), grid mode: one CTA per source pixel, the pixel's spectrum is
+// owned by the CTA (plain stores), I_ang by atomics.
+void launch_integrate_ase_owner(const DevProblem &P, const Chunk &c, const Handoff &h,
+                                const Outputs &o, cudaStream_t st);
+// Generic: one warp per ray slot, scatter binning with FP64 atomics (list mode, seeded mode,
+// non-identity owner maps) and/or per-ray dumps.
+void launch_integrate_scatter(const DevProblem &P, const Chunk &c, bool list_mode,
+                              const Handoff &h, const Outputs &o, cudaStream_t st);
+void launch_fp64_peak(double *out, int iters, cudaStream_t st, int *blocks, int *threads);
+
+} // namespace rtb

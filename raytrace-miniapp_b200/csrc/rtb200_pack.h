@@ -1,0 +1,282 @@
+// rtb200_pack.h — host-side re-layout of a create_image problem into ONE packed
+// structure-of-arrays blob (pure host C++, no CUDA calls).
+//
+// Replaces the reference's deep copy of an array-of-structs-of-pointers (7 cudaMalloc + 7
+// cudaMemcpy per gain plane, 10 + 10 for the seed: src/RayTraceImageCuda.cu:225-329) by one
+// contiguous buffer that is filled in pinned memory and uploaded with a single H2D copy.
+// Device pointers inside the blob are computed from the blob's device base address.
+//
+// Also tabulates everything that depends on a grid INDEX only, so that no libm call whose
+// result could differ between host and device libms is ever evaluated on the device:
+//   * tanf(1e-3f*a), tanf(1e-3f*b) for the start direction (RayTraceImageHelper.h:409-410);
+//   * the owner cell of each source coordinate for method 1 (getIndex, RayTraceImageCPU.cpp:11-16);
+//   * the separable seed factors for method 2 (calc_seed_inline / interp_pchip, :168-247).
+#pragma once
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+
+#include "../../include/rtb200.h"
+#include "rtb200_device.cuh"
+
+namespace rtb {
+
+// findfirstsingle (RayTraceImageHelper.h:101-117)
+inline size_t host_findfirstsingle(const double *X, size_t n, double Y)
+{
+    if (Y < X[0])
+        return 0;
+    if (Y > X[n - 1])
+        return n;
+    size_t lo = 0, hi = n - 1;
+    while (hi - lo != 1) {
+        size_t mid = (hi + lo) / 2;
+        if (X[mid] >= Y)
+            hi = mid;
+        else
+            lo = mid;
+    }
+    return hi;
+}
+
+// getIndex (RayTraceImageCPU.cpp:11-16)
+inline int host_get_index(int n, const double *x, double dx, double y)
+{
+    if (y < x[0] - 0.5 * dx || y > x[n - 1] + 0.5 * dx)
+        return -1;
+    return (int) host_findfirstsingle(x, (size_t) n, y - 0.5 * dx);
+}
+
+// interp_pchip (RayTraceImageHelper.h:168-220): monotone cubic Hermite interpolation.
+inline double host_interp_pchip(size_t N, const double *xi, const double *yi, double x)
+{
+    if (x <= xi[0] || N <= 2) {
+        double t = (x - xi[0]) / (xi[1] - xi[0]);
+        return (1.0 - t) * yi[0] + t * yi[1];
+    }
+    if (x >= xi[N - 1]) {
+        double t = (x - xi[N - 2]) / (xi[N - 1] - xi[N - 2]);
+        return (1.0 - t) * yi[N - 2] + t * yi[N - 1];
+    }
+    const size_t i = host_findfirstsingle(xi, N, x);
+    const double f1 = yi[i - 1], f2 = yi[i];
+    const double t = (x - xi[i - 1]) / (xi[i] - xi[i - 1]);
+    double g1 = 0, g2 = 0;
+    if (i <= 1) {
+        g1 = f2 - f1;
+    } else if ((f1 < f2 && f1 > yi[i - 2]) || (f1 > f2 && f1 < yi[i - 2])) {
+        const double f0 = yi[i - 2];
+        const double h1 = xi[i - 1] - xi[i - 2], h2 = xi[i] - xi[i - 1];
+        const double a1 = (h2 - h1) / h1, a2 = h1 / (h1 + h2);
+        g1 = a1 * (f1 - f0) + a2 * (f2 - f0);
+        const double s1 = std::fabs(f1 - f0) / h1, s2 = std::fabs(f2 - f1) / h2;
+        const double g_max = 2 * h2 * (s1 < s2 ? s1 : s2);
+        g1 = ((g1 >= 0) ? 1 : -1) * (std::fabs(g1) < g_max ? std::fabs(g1) : g_max);
+    }
+    if (i >= N - 1) {
+        g2 = f2 - f1;
+    } else if ((f2 < f1 && f2 > yi[i + 1]) || (f2 > f1 && f2 < yi[i + 1])) {
+        const double f0 = yi[i + 1];
+        const double h1 = xi[i] - xi[i - 1], h2 = xi[i + 1] - xi[i];
+        const double a1 = -h2 / (h1 + h2), a2 = (h2 - h1) / h2;
+        g2 = a1 * (f1 - f0) + a2 * (f2 - f0);
+        const double s1 = std::fabs(f2 - f1) / h1, s2 = std::fabs(f0 - f2) / h2;
+        const double g_max = 2 * h1 * (s1 < s2 ? s1 : s2);
+        g2 = ((g2 >= 0) ? 1 : -1) * (std::fabs(g2) < g_max ? std::fabs(g2) : g_max);
+    }
+    const double t2 = t * t;
+    return f1 + t2 * (2 * t - 3) * (f1 - f2) + t * g1 - t2 * (g1 + (1 - t) * (g1 + g2));
+}
+
+// Bump allocator over the staging blob.  With host == nullptr it only measures.
+class Blob {
+public:
+    Blob(char *host, const char *dev_base) : host_(host), dev_(dev_base), off_(0) {}
+    template <class T>
+    T *alloc(size_t n, const T **dev_ptr)
+    {
+        off_ = (off_ + 255) & ~size_t(255);
+        T *h = host_ ? reinterpret_cast<T *>(host_ + off_) : nullptr;
+        *dev_ptr = reinterpret_cast<const T *>(dev_ + off_);
+        off_ += n * sizeof(T);
+        return h;
+    }
+    size_t size() const { return (off_ + 255) & ~size_t(255); }
+    bool filling() const { return host_ != nullptr; }
+
+private:
+    char *host_;
+    const char *dev_;
+    size_t off_;
+};
+
+// Packs `p` into the blob.  Returns the number of bytes used; fills `out` (pointers relative
+// to dev_base).  explicit_rays: the ray list comes separately (rtb200_trace_rays), so only the
+// planes, the destination grid and dv are packed and method/scale are given by the caller.
+inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int method_in,
+                           double scale_in, char *host, const char *dev_base, DevProblem &out)
+{
+    Blob blob(host, dev_base);
+    const bool fill = blob.filling();
+    const rtb200_beam &e = *p.euv_beam;
+    const int N = p.N, K = e.nv;
+    std::memset(&out, 0, sizeof(out));
+    out.N = N;
+    out.K = K;
+    out.dz0 = (float) e.dz;
+    out.c = 0.5f;
+    out.use_emis = (p.gain[0].E0 != nullptr && p.seed == nullptr) ? 1 : 0; // :402
+
+    // ---- gain planes ------------------------------------------------------------------------
+    DevPlane *planes = blob.alloc<DevPlane>((size_t) N, &out.planes);
+    for (int ii = 0; ii < N; ii++) {
+        const rtb200_gain_plane &g = p.gain[ii];
+        const size_t nn = (size_t) g.Nx * g.Ny;
+        DevPlane P;
+        std::memset(&P, 0, sizeof(P));
+        double *x = blob.alloc<double>((size_t) g.Nx, &P.x);
+        double *y = blob.alloc<double>((size_t) g.Ny, &P.y);
+        Node *node = blob.alloc<Node>(nn, &P.node);
+        float *gv = blob.alloc<float>(nn * (size_t) K, &P.gv);
+        if (fill) {
+            std::memcpy(x, g.x, sizeof(double) * g.Nx);
+            std::memcpy(y, g.y, sizeof(double) * g.Ny);
+            for (size_t q = 0; q < nn; q++) {
+                node[q].n = g.n[q];
+                node[q].g0 = g.g0[q];
+                node[q].E0 = g.E0 ? g.E0[q] : 0.0f;
+            }
+            std::memcpy(gv, g.gv, sizeof(float) * nn * (size_t) K);
+            P.Nx = g.Nx;
+            P.Ny = g.Ny;
+            P.range[0] = (float) g.x[0]; // :445-453
+            P.range[1] = (float) g.x[g.Nx - 1];
+            P.range[2] = (float) g.y[0];
+            P.range[3] = (float) g.y[g.Ny - 1];
+            P.abs_y = 0;
+            if (P.range[2] >= 0) {
+                P.range[2] = -P.range[3];
+                P.abs_y = 1;
+            }
+            P.x0 = g.x[0];
+            P.y0 = g.y[0];
+            P.inv_dx = g.Nx > 1 ? (double) (g.Nx - 1) / (g.x[g.Nx - 1] - g.x[0]) : 0.0;
+            P.inv_dy = g.Ny > 1 ? (double) (g.Ny - 1) / (g.y[g.Ny - 1] - g.y[0]) : 0.0;
+            planes[ii] = P;
+        }
+    }
+
+    // ---- destination grid (euv_beam) --------------------------------------------------------
+    out.nx = e.nx;
+    out.ny = e.ny;
+    out.na = e.na;
+    out.nb = e.nb;
+    out.edx = e.dx;
+    out.edy = e.dy;
+    out.eda = e.da;
+    out.edb = e.db;
+    out.y_mirror = (e.ny > 0 && e.y && e.y[0] >= 0.0) ? 1 : 0;
+    double *ex = blob.alloc<double>((size_t) e.nx, &out.ex);
+    double *ey = blob.alloc<double>((size_t) e.ny, &out.ey);
+    double *ea = blob.alloc<double>((size_t) e.na, &out.ea);
+    double *eb = blob.alloc<double>((size_t) e.nb, &out.eb);
+    double *dv2 = blob.alloc<double>((size_t) K, &out.dv2);
+    if (fill) {
+        if (e.nx > 0)
+            std::memcpy(ex, e.x, sizeof(double) * e.nx);
+        if (e.ny > 0)
+            std::memcpy(ey, e.y, sizeof(double) * e.ny);
+        if (e.na > 0)
+            std::memcpy(ea, e.a, sizeof(double) * e.na);
+        if (e.nb > 0)
+            std::memcpy(eb, e.b, sizeof(double) * e.nb);
+        for (int k = 0; k < K; k++)
+            dv2[k] = e.dv ? 2.0 * e.dv[k] : 0.0; // RayTraceImageCPU.cpp:66: (2.0*dv[iv])*Iv[iv]
+    }
+    if (p.seed) {
+        double *fv = blob.alloc<double>((size_t) p.seed->dim[4], &out.seed_fv);
+        if (fill)
+            std::memcpy(fv, p.seed->f[4], sizeof(double) * p.seed->dim[4]);
+        out.seed_f0 = p.seed->f0;
+    }
+    if (explicit_rays) {
+        out.method = method_in;
+        out.scale = scale_in;
+        return blob.size();
+    }
+
+    // ---- ray source grid (src/RayTraceImage.cpp:277-328) ------------------------------------
+    const rtb200_beam &sz = p.seed ? *p.seed_beam : e;                 // sizes follow `seed`
+    const rtb200_beam &sc = p.seed_beam ? *p.seed_beam : *p.euv_beam; // coordinates follow `seed_beam`
+    if (p.seed) {
+        out.method = 2;
+        out.scale = (sz.dx * sz.dy * sz.da * sz.db) / (e.dx * e.dy);
+    } else {
+        out.method = 1;
+        out.scale = 1.0;
+    }
+    out.snx = sz.nx;
+    out.sny = sz.ny;
+    out.sna = sz.na;
+    out.snb = sz.nb;
+    out.n_start = p.N_start;
+    out.n_parallel = p.N_parallel;
+    const long long AB = (long long) sz.na * sz.nb;
+    out.ab_max = (int) ((AB + p.N_parallel - 1) / p.N_parallel);
+    float *sxf = blob.alloc<float>((size_t) sz.nx, &out.sxf);
+    float *syf = blob.alloc<float>((size_t) sz.ny, &out.syf);
+    float *saf = blob.alloc<float>((size_t) sz.na, &out.saf);
+    float *sbf = blob.alloc<float>((size_t) sz.nb, &out.sbf);
+    float *tanA = blob.alloc<float>((size_t) sz.na, &out.tanA);
+    float *tanB = blob.alloc<float>((size_t) sz.nb, &out.tanB);
+    int *pixI = blob.alloc<int>((size_t) sz.nx, &out.pixI);
+    int *pixJ = blob.alloc<int>((size_t) sz.ny, &out.pixJ);
+    int *binA = blob.alloc<int>((size_t) sz.na, &out.binA);
+    int *binB = blob.alloc<int>((size_t) sz.nb, &out.binB);
+    if (fill) {
+        for (int i = 0; i < sz.nx; i++) {
+            sxf[i] = (float) sc.x[i];
+            pixI[i] = host_get_index(e.nx, e.x, e.dx, (double) sxf[i]);
+        }
+        for (int i = 0; i < sz.ny; i++) {
+            syf[i] = (float) sc.y[i];
+            pixJ[i] = host_get_index(e.ny, e.y, e.dy, (double) syf[i]);
+        }
+        for (int i = 0; i < sz.na; i++) {
+            saf[i] = (float) sc.a[i];
+            tanA[i] = tanf(1e-3f * saf[i]);
+            binA[i] = host_get_index(e.na, e.a, e.da, (double) saf[i]);
+        }
+        for (int i = 0; i < sz.nb; i++) {
+            sbf[i] = (float) sc.b[i];
+            tanB[i] = tanf(1e-3f * sbf[i]);
+            binB[i] = host_get_index(e.nb, e.b, e.db, (double) sbf[i]);
+        }
+    }
+    if (p.seed) {
+        // method 2: calc_seed_inline(seed, ray.x, ray.y, ray.a, ray.b) depends on the source
+        // indices only.  NaN marks "outside the seed grid" (whole product becomes f = 0).
+        const rtb200_seed &s = *p.seed;
+        const double nan = std::numeric_limits<double>::quiet_NaN();
+        double *f[4];
+        f[0] = blob.alloc<double>((size_t) sz.nx, &out.seed_fx);
+        f[1] = blob.alloc<double>((size_t) sz.ny, &out.seed_fy);
+        f[2] = blob.alloc<double>((size_t) sz.na, &out.seed_fa);
+        f[3] = blob.alloc<double>((size_t) sz.nb, &out.seed_fb);
+        if (fill) {
+            const int n[4] = { sz.nx, sz.ny, sz.na, sz.nb };
+            const float *src[4] = { sxf, syf, saf, sbf };
+            for (int d = 0; d < 4; d++)
+                for (int i = 0; i < n[d]; i++) {
+                    const double v = (double) src[d][i];
+                    const bool inside = v >= s.x[d][0] && v <= s.x[d][s.dim[d] - 1];
+                    f[d][i] = inside ? host_interp_pchip((size_t) s.dim[d], s.x[d], s.f[d], v) : nan;
+                }
+        }
+    }
+    return blob.size();
+}
+
+} // namespace rtb

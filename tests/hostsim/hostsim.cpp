@@ -1,0 +1,112 @@
+// hostsim.cpp — TEST-ONLY build of the march's device functions for the host.
+//
+// rtb200_march.cuh / rtb200_pack.h are written as __host__ __device__ / plain C++ so that the
+// exact same source the GPU runs can be unit-tested here, without a GPU, against the CPU oracle
+// (tests/test_march_hostsim.py).  This library is NOT part of librtb200.so, is not reachable
+// from the product API and is not a CPU fallback: it exists so that `pytest -m "not gpu"`
+// can check the march logic (index search, sub-segment bookkeeping, packing) bit for bit.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../raytrace-miniapp_b200/csrc/rtb200_pack.h"
+
+using namespace rtb;
+
+namespace {
+struct ArraySink {
+    float *gvl, *evl;
+    int *ivl;
+    void operator()(int idx, float g, float e, int cell) const
+    {
+        gvl[idx] = g;
+        evl[idx] = e;
+        ivl[idx] = cell;
+    }
+};
+} // namespace
+
+extern "C" {
+
+// Packs the problem exactly as the product does (host pointers instead of device pointers) and
+// marches rays [first, first+count) of the grid enumeration.  Outputs: gvl/evl/ivl
+// [count][(N-1)*3] (zero outside the visited range), exit [count][6] = pos.x, pos.y, s.x, s.y,
+// s.z, escaped; meta [count][2] = seg_lo, seg_hi.  Returns total march steps, or -1.
+long long hostsim_march(const rtb200_problem *p, long long first, long long count, float *gvl,
+                        float *evl, int *ivl, float *exit_state, int *meta)
+{
+    DevProblem P;
+    const size_t bytes = pack_problem(*p, false, 0, 0.0, nullptr, nullptr, P);
+    std::vector<char> blob(bytes + 256);
+    char *base = (char *) (((uintptr_t) blob.data() + 255) & ~(uintptr_t) 255);
+    pack_problem(*p, false, 0, 0.0, base, base, P);
+    const int S = (P.N - 1) * RTB_N_SUB;
+    long long steps_total = 0;
+    const long long AB = (long long) P.sna * P.snb;
+    for (long long r = 0; r < count; r++) {
+        const long long ijkm = P.n_start + (first + r) * P.n_parallel;
+        if (ijkm >= (long long) P.snx * P.sny * AB)
+            return -1;
+        const int m = (int) (ijkm % P.snb);
+        const int k = (int) ((ijkm / P.snb) % P.sna);
+        const int j = (int) ((ijkm / AB) % P.sny);
+        const int i = (int) (ijkm / (AB * P.sny));
+        std::memset(gvl + r * S, 0, sizeof(float) * S);
+        std::memset(evl + r * S, 0, sizeof(float) * S);
+        std::memset(ivl + r * S, 0, sizeof(int) * S);
+        ArraySink sink{ gvl + r * S, evl + r * S, ivl + r * S };
+        MarchResult res;
+        unsigned steps = 0;
+        march_ray(P.planes, P.N, P.method, P.dz0, P.c, P.use_emis != 0, P.sxf[i], P.syf[j],
+                  P.tanA[k], P.tanB[m], sink, res, steps);
+        steps_total += steps;
+        float *e = exit_state + r * 6;
+        e[0] = res.pos.x;
+        e[1] = res.pos.y;
+        e[2] = res.s.x;
+        e[3] = res.s.y;
+        e[4] = res.s.z;
+        e[5] = (float) res.escaped;
+        meta[2 * r] = res.seg_lo;
+        meta[2 * r + 1] = res.seg_hi;
+    }
+    return steps_total;
+}
+
+// Table doors (host packing logic): owner tables and seed factors for the grid enumeration.
+int hostsim_tables(const rtb200_problem *p, int *pixI, int *pixJ, int *binA, int *binB,
+                   float *tanA, float *tanB, double *seed_f /* nx+ny+na+nb or null */)
+{
+    DevProblem P;
+    const size_t bytes = pack_problem(*p, false, 0, 0.0, nullptr, nullptr, P);
+    std::vector<char> blob(bytes + 256);
+    char *base = (char *) (((uintptr_t) blob.data() + 255) & ~(uintptr_t) 255);
+    pack_problem(*p, false, 0, 0.0, base, base, P);
+    std::memcpy(pixI, P.pixI, sizeof(int) * P.snx);
+    std::memcpy(pixJ, P.pixJ, sizeof(int) * P.sny);
+    std::memcpy(binA, P.binA, sizeof(int) * P.sna);
+    std::memcpy(binB, P.binB, sizeof(int) * P.snb);
+    std::memcpy(tanA, P.tanA, sizeof(float) * P.sna);
+    std::memcpy(tanB, P.tanB, sizeof(float) * P.snb);
+    if (seed_f && P.seed_fx) {
+        std::memcpy(seed_f, P.seed_fx, sizeof(double) * P.snx);
+        std::memcpy(seed_f + P.snx, P.seed_fy, sizeof(double) * P.sny);
+        std::memcpy(seed_f + P.snx + P.sny, P.seed_fa, sizeof(double) * P.sna);
+        std::memcpy(seed_f + P.snx + P.sny + P.sna, P.seed_fb, sizeof(double) * P.snb);
+    }
+    return P.method;
+}
+
+double hostsim_pchip(size_t N, const double *xi, const double *yi, double x)
+{
+    return host_interp_pchip(N, xi, yi, x);
+}
+int hostsim_get_index(int n, const double *x, double dx, double y) { return host_get_index(n, x, dx, y); }
+int hostsim_find_cell(const double *X, int n, double Y)
+{
+    double xl, xr;
+    const double inv = n > 1 ? (double) (n - 1) / (X[n - 1] - X[0]) : 0.0;
+    return find_cell(X, n, X[0], inv, Y, xl, xr);
+}
+
+} // extern "C"

@@ -1,0 +1,179 @@
+"""Parity of the CUDA path (through the C ABI of include/rtb200.h) against the CPU oracle and
+the committed reference outputs.  Tolerances: march intermediates bit-exact; image / I_ang
+relative L2 <= 1e-10 and max element-wise relative error <= 1e-9 over entries > 1e-6*max
+(BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from raytrace_miniapp_b200 import abi
+from conftest import max_rel, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_L2 = 1e-10
+TOL_MAX = 1e-9
+
+
+def check_image(got, want):
+    assert rel_l2(got[0], want[0]) <= TOL_L2, ("image relL2", rel_l2(got[0], want[0]))
+    assert rel_l2(got[1], want[1]) <= TOL_L2, ("I_ang relL2", rel_l2(got[1], want[1]))
+    assert max_rel(got[0], want[0]) <= TOL_MAX, ("image max rel", max_rel(got[0], want[0]))
+    assert max_rel(got[1], want[1]) <= TOL_MAX, ("I_ang max rel", max_rel(got[1], want[1]))
+
+
+def test_march_intermediates_bit_exact(ase_small, oracle, ctx):
+    """gvl / evl / ivl of >= 10^4 rays are bit-identical to the oracle's (FP32 march)."""
+    p, _ = ase_small
+    rays = p.rays()[3::37]
+    assert rays.size >= 10000
+    g = ctx.calc_rays(p, rays)
+    o = oracle.calc_rays(p, rays)
+    assert np.array_equal(g["error"], o["error"])
+    assert np.array_equal(g["gvl"].view(np.uint32), o["gvl"].view(np.uint32))
+    assert np.array_equal(g["evl"].view(np.uint32), o["evl"].view(np.uint32))
+    assert np.array_equal(g["ivl"], o["ivl"])
+    ok = o["error"] == 0
+    assert np.array_equal(g["ray2"]["x"][ok], o["ray2"]["x"][ok])
+    assert np.array_equal(g["ray2"]["y"][ok], o["ray2"]["y"][ok])
+    # per-ray spectra: FP64, libm exp differs by <= 1 ulp between host and device
+    scale = np.abs(o["Iv"]).max(axis=1, keepdims=True) + 1e-300
+    assert np.max(np.abs(g["Iv"] - o["Iv"]) / scale) < 1e-12
+
+
+def test_exit_angles_bit_exact(ase_small, seed_small, oracle, ctx):
+    """ray2.a / ray2.b = atanf(s.x/s.z)*1e3f feed a discrete bin in seeded mode."""
+    for (p, _), sl in ((ase_small, slice(5, None, 211)), (seed_small, slice(7, None, 4001))):
+        rays = p.rays()[sl]
+        p2 = abi.Problem(p.euv_beam, p.gain)  # calc_rays without the seed: march only
+        g = ctx.calc_rays(p2, rays, method=p.method)
+        o = oracle.calc_rays(p2, rays, method=p.method)
+        ok = o["error"] == 0
+        for f in "xyab":
+            assert np.array_equal(g["ray2"][f][ok].view(np.uint32), o["ray2"][f][ok].view(np.uint32)), f
+
+
+def test_ase_small_image_vs_oracle_and_reference(ase_small, oracle, ctx):
+    p, extra = ase_small
+    img, ang = ctx.create_image(p)
+    assert ctx.failure_code == 0
+    o = oracle.create_image(p)
+    check_image((img, ang), (o["image"], o["I_ang"]))
+    check_image((img, ang), (extra["ref_cpu_image"], extra["ref_cpu_I_ang"]))
+    # the reference's own acceptance test (check_ans, src/CreateImageHelpers.cpp:66-100)
+    g0, g1 = np.linalg.norm(extra["dat_golden_image"]), np.linalg.norm(img)
+    assert (g0 - g1) / g0 <= 5e-6
+    t = ctx.timings()
+    assert t["kernel_launches"] >= 2 and t["march_ms"] > 0 and t["integrate_ms"] > 0
+
+
+def test_seed_small_image_vs_reference(seed_small, ctx):
+    p, extra = seed_small
+    img, ang = ctx.create_image(p)
+    assert ctx.failure_code == 0
+    check_image((img, ang), (extra["ref_cpu_image"], extra["ref_cpu_I_ang"]))
+
+
+def test_strided_decomposition(ase_small, oracle, ctx):
+    """N_start / N_parallel (src/RayTraceImage.cpp:300-308): each worker matches the oracle and
+    the workers add up to the full image."""
+    p, extra = ase_small
+    tot_i, tot_a = 0, 0
+    try:
+        for start in range(3):
+            p.N_start, p.N_parallel = start, 3
+            img, ang = ctx.create_image(p)
+            tot_i, tot_a = tot_i + img, tot_a + ang
+            if start == 1:
+                o = oracle.create_image(p)
+                check_image((img, ang), (o["image"], o["I_ang"]))
+    finally:
+        p.N_start, p.N_parallel = 0, 1
+    check_image((tot_i, tot_a), (extra["ref_cpu_image"], extra["ref_cpu_I_ang"]))
+
+
+def test_explicit_ray_list_accumulates(ase_small, oracle, ctx):
+    """RayTraceImage<B200>Loop semantics: arbitrary ray list, += into caller buffers."""
+    p, _ = ase_small
+    rays = p.rays()[::53]
+    o = oracle.trace_rays(p, rays, 1, 1.0)
+    img = np.full(o["image"].size, 1.0)
+    ang = np.full(o["I_ang"].size, 2.0)
+    ctx.trace_rays(p, rays, 1, 1.0, image=img, I_ang=ang)
+    check_image((img - 1.0, ang - 2.0), (o["image"], o["I_ang"]))
+    # empty list: nothing added, no error
+    ctx.trace_rays(p, rays[:0], 1, 1.0, image=img, I_ang=ang)
+    check_image((img - 1.0, ang - 2.0), (o["image"], o["I_ang"]))
+
+
+def test_failures_are_reported_like_the_reference(ase_small, oracle, ctx, rtlib):
+    """Negative emissivity cannot occur (clamped) but a NaN gain makes rays fail with code -3;
+    failed rays are excluded from the image and listed (src/RayTraceImageCPU.cpp:32-36)."""
+    p, _ = ase_small
+    g = p.gain[2]
+    saved = g.g0.copy()
+    g.g0[5:8, 40:60] = np.nan
+    p.N_parallel = 11
+    try:
+        o = oracle.create_image(p)
+        assert o["failure_code"] == 8 and o["n_failed"] > 0
+        img, ang = ctx.create_image(p, raise_on_failed=False)
+        assert ctx.failure_code == o["failure_code"]
+        assert ctx.n_failed == o["n_failed"]
+        check_image((img, ang), (o["image"], o["I_ang"]))
+        got = set(map(tuple, ctx.failed.view(np.float32).reshape(-1, 4).tolist()))
+        allf = set(map(tuple, p.rays().view(np.float32).reshape(-1, 4).tolist()))
+        assert got and got <= allf
+        with pytest.raises(rtlib.RaysFailed):
+            ctx.create_image(p)
+    finally:
+        g.g0[:] = saved
+        p.N_parallel = 1
+
+
+def test_limits_and_grid_errors(ase_small, ctx, rtlib):
+    p, _ = ase_small
+    x = p.euv_beam.x
+    p.euv_beam.x = x.copy()
+    p.euv_beam.x[7] *= 1.0 + 1e-9
+    try:
+        with pytest.raises(rtlib.RTB200Error) as e:
+            ctx.create_image(p)
+        assert e.value.code == abi.ERR_GRID and "uniform grid" in str(e.value)
+    finally:
+        p.euv_beam.x = x
+    many = abi.Problem(p.euv_beam, [p.gain[i % 3] for i in range(21)])
+    with pytest.raises(rtlib.RTB200Error) as e:
+        ctx.create_image(many)
+    assert e.value.code == abi.ERR_LIMITS
+
+
+def test_single_plane_problem_is_empty(ase_small, ctx, oracle):
+    """N = 1: no length segments, the image is identically zero."""
+    p, _ = ase_small
+    one = abi.Problem(p.euv_beam, p.gain[:1])
+    one.N_parallel = 17
+    img, ang = ctx.create_image(one)
+    assert not img.any() and not ang.any()
+    o = oracle.create_image(one)
+    assert not o["image"].any()
+
+
+def test_device_tiles_equal_whole_image(ase_small, ctx):
+    """Pixel-tile sharding (the multi-GPU decomposition) on one device: tiles reproduce the
+    single-launch image bit for bit in ASE mode (disjoint pixels, same per-pixel order)."""
+    import torch
+    p, _ = ase_small
+    e = p.euv_beam
+    n = ctx.stage(p)
+    assert n == e.nx * e.ny and ctx.staged_rays == p.n_rays
+    whole_i = torch.zeros(e.nx * e.ny * e.nv, dtype=torch.float64, device="cuda")
+    whole_a = torch.zeros(e.na * e.nb, dtype=torch.float64, device="cuda")
+    ctx.launch(0, n, whole_i, whole_a)
+    ctx.sync()
+    tile_i, tile_a = torch.zeros_like(whole_i), torch.zeros_like(whole_a)
+    cuts = [0, 100, 101, n // 2, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        ctx.launch(a, b, tile_i, tile_a)
+    ctx.sync()
+    assert torch.equal(tile_i, whole_i)
+    assert rel_l2(tile_a.cpu().numpy(), whole_a.cpu().numpy()) < 1e-14
