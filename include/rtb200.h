@@ -165,14 +165,17 @@ int rtb200_launch(rtb200_ctx *ctx, int64_t pix_begin, int64_t pix_end, double *d
 int rtb200_sync(rtb200_ctx *ctx, unsigned *failure_code, rtb200_ray *failed, int max_failed,
                 int *n_failed);
 int rtb200_get_timings(const rtb200_ctx *ctx, rtb200_timings *out);
+/* Forget the launches recorded so far: the timings returned after the next rtb200_sync then
+ * cover exactly the launches issued in between (used to time a series of steps). */
+int rtb200_reset_timings(rtb200_ctx *ctx);
 
 /* ---- wire format ---------------------------------------------------------------------------- */
 
 /* Parse a serialized create_image_struct (the payload of a .dat file after its uint64 length,
  * src/CreateImage.cpp:26-58; format src/RayTraceStructures.cpp:2159-2292 and the nested
- * pack() functions) into a problem whose arrays point INTO `bytes` (zero copy; arrays are
- * memcpy-aligned copies only where the stream is misaligned).  golden_image / golden_I_ang
- * receive pointers to the embedded golden arrays or NULL.  Free with rtb200_free_problem. */
+ * pack() functions) into a problem that owns copies of the arrays on the path (the byte
+ * stream is not aligned).  golden_image / golden_I_ang receive pointers to the embedded
+ * golden arrays or NULL.  Free everything with rtb200_free_problem. */
 int rtb200_parse_dat(const void *bytes, size_t n_bytes, rtb200_problem **problem,
                      const double **golden_image, const double **golden_I_ang);
 void rtb200_free_problem(rtb200_problem *problem);

@@ -491,6 +491,14 @@ int rtb200_sync(rtb200_ctx *ctx, unsigned *failure_code, rtb200_ray *failed, int
     return finish(ctx, failure_code, failed, max_failed, n_failed);
 }
 
+int rtb200_reset_timings(rtb200_ctx *ctx)
+{
+    if (!ctx)
+        return RTB200_ERR_ARG;
+    reset_timing(ctx);
+    return RTB200_OK;
+}
+
 int rtb200_get_timings(const rtb200_ctx *ctx, rtb200_timings *out)
 {
     if (!ctx || !out)

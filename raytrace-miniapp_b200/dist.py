@@ -1,0 +1,56 @@
+"""Image-tile sharding of one create_image call over the ranks of a torch.distributed group.
+
+One process per GPU.  The unit of sharding is the source pixel (rows of the image are the
+sharded axis): rank r traces the contiguous pixel range tile_bounds(n, world, r) and owns those
+image rows exclusively (ASE).  The exchange step that follows the kernels is the one the full
+application performs over MPI (intensity_step_struct::sum_reduce,
+src/RayTraceStructures.cpp:1603-1646), restated for device-resident partials:
+  ASE    : all_gather of the equal-sized image tiles + all_reduce(sum) of I_ang
+  seeded : all_reduce(sum) of the full image and of I_ang (scatter binning)
+over NCCL / NVLink on GPUs, gloo in the CPU tests.
+"""
+import torch
+import torch.distributed as dist
+
+
+def tile_bounds(n_pixels, world, rank):
+    """Equal contiguous tiles of ceil(n/world) pixels; the last ones may be short or empty."""
+    per = (n_pixels + world - 1) // world
+    lo = min(n_pixels, rank * per)
+    return lo, min(n_pixels, lo + per), per
+
+
+def exchange(image, I_ang, n_pixels, nv, method, group=None):
+    """In-place exchange of the partial results.  image: flat [n_pixels*nv] tensor holding this
+    rank's owned rows (ASE) or its partial sums (seeded); I_ang: flat partial sums."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return image, I_ang
+    if method == 1:
+        rank = dist.get_rank(group)
+        lo, hi, per = tile_bounds(n_pixels, world, rank)
+        if per * world == n_pixels:
+            dist.all_gather_into_tensor(image, image[lo * nv:hi * nv].clone(), group=group)
+        else:  # ragged: gather padded tiles, then trim
+            pad = torch.zeros(per * nv, dtype=image.dtype, device=image.device)
+            pad[:(hi - lo) * nv] = image[lo * nv:hi * nv]
+            full = torch.empty(world * per * nv, dtype=image.dtype, device=image.device)
+            dist.all_gather_into_tensor(full, pad, group=group)
+            image.copy_(full[:n_pixels * nv])
+    else:
+        dist.all_reduce(image, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(I_ang, op=dist.ReduceOp.SUM, group=group)
+    return image, I_ang
+
+
+def sharded_create_image(ctx, problem, image, I_ang, group=None, stream=None):
+    """Stage-free step: `ctx` already holds the staged problem.  Zeroes the buffers, traces this
+    rank's tile on `stream` (default: torch's current stream) and exchanges.  Asynchronous."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = ctx.staged_pixels
+    lo, hi, _ = tile_bounds(n, world, rank)
+    image.zero_()
+    I_ang.zero_()
+    st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+    ctx.launch(lo, hi, image, I_ang, stream=st)
+    return exchange(image, I_ang, n, problem.euv_beam.nv, problem.method, group)

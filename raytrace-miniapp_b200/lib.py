@@ -75,6 +75,7 @@ def load():
     L.rtb200_launch.argtypes = [ctx, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.rtb200_sync.argtypes = [ctx, P(C.c_uint), P(abi.Ray), C.c_int, P(C.c_int)]
     L.rtb200_get_timings.argtypes = [ctx, P(abi.Timings)]
+    L.rtb200_reset_timings.argtypes = [ctx]
     L.rtb200_parse_dat.argtypes = [C.c_void_p, C.c_size_t, P(P(abi.CProblem)),
                                    P(abi.c_double_p), P(abi.c_double_p)]
     L.rtb200_free_problem.argtypes = [P(abi.CProblem)]
@@ -202,10 +203,14 @@ class Context:
     def staged_rays(self):
         return self.L.rtb200_staged_rays(self.h)
 
-    def launch(self, pix_begin, pix_end, d_image, d_I_ang, stream=0):
-        """d_image / d_I_ang: device buffers (torch CUDA tensors or raw addresses)."""
+    def launch(self, pix_begin, pix_end, d_image, d_I_ang, stream=None):
+        """d_image / d_I_ang: device buffers (torch CUDA tensors or raw addresses).  stream:
+        None = the context's own stream; else a cudaStream_t handle (0, torch's handle of the
+        legacy default stream, is passed as cudaStreamLegacy)."""
+        if stream is not None and stream == 0:
+            stream = 1  # cudaStreamLegacy
         self._check(self.L.rtb200_launch(self.h, pix_begin, pix_end, _addr(d_image),
-                                         _addr(d_I_ang), stream or None))
+                                         _addr(d_I_ang), stream))
 
     def sync(self, raise_on_failed=True):
         fc, nf = C.c_uint(0), C.c_int(0)
@@ -218,6 +223,9 @@ class Context:
         if rc == abi.RAYS_FAILED and raise_on_failed:
             raise RaysFailed(fc.value, self.failed)
         return rc
+
+    def reset_timings(self):
+        self._check(self.L.rtb200_reset_timings(self.h))
 
     def timings(self):
         t = abi.Timings()
