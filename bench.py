@@ -160,7 +160,9 @@ def run_reference(args):
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from raytrace_miniapp_b200 import dist as rdist, lib as rl
+    from raytrace_miniapp_b200 import build as rbuild, dist as rdist, lib as rl
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        rbuild.build_library()  # no-op when librtb200.so is newer than its sources
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -1,0 +1,122 @@
+// rtb200_fp64.cuh — the FP64 frequency-bin update of the integration kernels.
+//
+// One update of one frequency bin over one (length segment, sub-segment)
+// (src/common/RayTraceImageHelper.h:549-557):
+//     gl = gvl*gv[k], el = evl*gv[k]                  (float products, widened afterwards)
+//     |gl| < 1e-3 :  I = el*(1 + gl/2*(1 + 0.3333333333*gl)) + I*(1 + gl*(1 + gl/2))
+//     otherwise   :  I = el/gl*(exp(gl) - 1) + I*exp(gl)
+// The stated tolerance of the path is 1e-10 relative on the image, so exp and the division are
+// evaluated to ~2e-16 / ~2e-14 relative with a fraction of the instructions of the IEEE library
+// routines (which cost 18 + 10 FP64 instructions plus slow-path branches):
+//   exp : x = (64 m + j) ln2/64 + r,  exp(x) = 2^m * 2^(j/64) * (1 + r*q(r)),  |r| <= ln2/128,
+//         2^(j/64) from a 64-entry table, q of degree 4  -> 10 FP64 instructions;
+//   1/gl: single-precision reciprocal seed + one Newton step in double -> 2 FP64 instructions.
+// Written __host__ __device__ so tests/hostsim can check it against libm without a GPU.
+#pragma once
+#include "rtb200_exptab.h"
+#include "rtb200_math.cuh"
+
+namespace rtb {
+
+#define RTB_EXP_MAGIC 6755399441055744.0 /* 1.5 * 2^52: round-to-nearest-integer by addition */
+
+// Constants of the update.  On the device they are read as constant-bank operands (no
+// per-use materialisation of 64-bit immediates); the host build uses the same values.
+#define RTB_K_64_OVER_LN2 0
+#define RTB_K_LN2_64_HI 1
+#define RTB_K_LN2_64_LO 2
+#define RTB_K_C5 3
+#define RTB_K_C4 4
+#define RTB_K_C3 5
+#define RTB_K_THIRD 6
+#define RTB_K_VALUES                                                                             \
+    RTB_EXP_64_OVER_LN2, -RTB_EXP_LN2_64_HI, -RTB_EXP_LN2_64_LO, 1.0 / 120.0, 1.0 / 24.0,        \
+        1.0 / 6.0, 0.3333333333, 0.0
+#if defined(__CUDACC__)
+__constant__ double c_fp64_k[8] = { RTB_K_VALUES };
+#endif
+#if defined(__CUDA_ARCH__)
+#define RTB_K(i) c_fp64_k[i]
+#else
+static const double h_fp64_k[8] = { RTB_K_VALUES };
+#define RTB_K(i) h_fp64_k[i]
+#endif
+
+RTB_HD double fma64(double a, double b, double c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return fma(a, b, c);
+#endif
+}
+
+RTB_HD int lo32(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2loint(x);
+#else
+    long long b;
+    memcpy(&b, &x, 8);
+    return (int) (unsigned) (b & 0xffffffffLL);
+#endif
+}
+
+RTB_HD double scale_pow2(double e, int m) // e * 2^m for a normal e and a normal result
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(e) + (m << 20), __double2loint(e));
+#else
+    long long b;
+    memcpy(&b, &e, 8);
+    b += (long long) m << 52;
+    memcpy(&e, &b, 8);
+    return e;
+#endif
+}
+
+// exp(x) for |x| < 700 (the caller routes everything else to the library exp).
+// T: 64-entry table of 2^(j/64) (shared memory on the device).
+RTB_HD double exp_core(double x, const double *T)
+{
+    const double t = fma64(x, RTB_K(RTB_K_64_OVER_LN2), RTB_EXP_MAGIC);
+    const int n = lo32(t);
+    const double tn = t - RTB_EXP_MAGIC;
+    double r = fma64(tn, RTB_K(RTB_K_LN2_64_HI), x);
+    r = fma64(tn, RTB_K(RTB_K_LN2_64_LO), r);
+    double q = fma64(r, RTB_K(RTB_K_C5), RTB_K(RTB_K_C4));
+    q = fma64(r, q, RTB_K(RTB_K_C3));
+    q = fma64(r, q, 0.5);
+    q = fma64(r, q, 1.0);
+    const double Tj = T[n & 63];
+    const double e = fma64(Tj, r * q, Tj);
+    return scale_pow2(e, n >> 6);
+}
+
+RTB_HD double exp_any(double x, const double *T)
+{
+    if (fabs(x) < 700.0)
+        return exp_core(x, T);
+    return exp(x); // overflow / underflow / NaN: the library routine's semantics
+}
+
+// The |gl| < 1e-3 branch.
+RTB_HD double ase_update_small(double Iv, double gl, double el)
+{
+    const double a = fma64(gl, RTB_K(RTB_K_THIRD), 1.0);
+    const double c = fma64(0.5 * gl, a, 1.0);
+    const double d = fma64(gl, 0.5, 1.0);
+    const double e = fma64(gl, d, 1.0);
+    return fma64(el, c, Iv * e);
+}
+
+// The exp branch for |gl| < 700; rcp_seed is a single-precision approximation of 1/gl.
+RTB_HD double ase_update_large(double Iv, double gl, double el, float rcp_seed, const double *T)
+{
+    const double e = exp_core(gl, T);
+    const double r0 = (double) rcp_seed;
+    const double r1 = fma64(r0, fma64(-gl, r0, 1.0), r0); // 1/gl to ~2^-46
+    return fma64(el * r1, e - 1.0, Iv * e);
+}
+
+} // namespace rtb

@@ -117,6 +117,9 @@ struct rtb200_ctx {
     rtb200_timings last;
     int launches = 0;
     bool count_steps = false;
+    bool use_fused = false; // opt-in (RTB200_FUSED=1): measured slower than the two-kernel path
+    bool flat_march = true;
+    unsigned long long *d_work = nullptr;
     size_t handoff_bytes = 256u << 20;
 };
 
@@ -295,6 +298,16 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
     const DevProblem &P = ctx->prob;
     if (pix1 <= pix0)
         return RTB200_OK;
+    if (ctx->owner_ok && !out.Iv && !out.error && ctx->use_fused) {
+        const size_t e0 = new_event(ctx, st);
+        if (launch_trace_ase_fused(P, pix0, pix1, out, st)) {
+            const size_t e1 = new_event(ctx, st);
+            ctx->ev_integ.push_back({ e0, e1 }); // one kernel: reported under integrate_ms
+            ctx->launches += 1;
+            RTB_CUDA(cudaGetLastError());
+            return RTB200_OK;
+        }
+    }
     const int S = (P.N - 1) * RTB_N_SUB;
     const bool need_exit = P.method != 1;
     const size_t per_slot = (size_t) std::max(S, 1) * sizeof(SegRec) + sizeof(unsigned) +
@@ -312,7 +325,7 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
         c.pix0 = a;
         c.pix1 = std::min(pix1, a + pix_per_chunk);
         const size_t e0 = new_event(ctx, st);
-        launch_march(P, c, false, h, ctx->d_fail, ctx->count_steps, st);
+        launch_march(P, c, false, h, ctx->d_fail, ctx->count_steps, st, ctx->d_work, ctx->flat_march);
         const size_t e1 = new_event(ctx, st);
         if (ctx->owner_ok && !out.Iv && !out.error)
             launch_integrate_ase_owner(P, c, h, out, st);
@@ -401,11 +414,17 @@ int rtb200_create(int device, rtb200_ctx **out)
         return fail(e);
     if ((e = cudaMallocHost((void **) &ctx->h_fail, sizeof(FailState))) != cudaSuccess)
         return fail(e);
+    if ((e = cudaMalloc((void **) &ctx->d_work, sizeof(unsigned long long))) != cudaSuccess)
+        return fail(e);
     std::memset(ctx->h_fail, 0, sizeof(FailState));
     if (const char *s = getenv("RTB200_HANDOFF_MB"))
         ctx->handoff_bytes = (size_t) std::max(1, atoi(s)) << 20;
     if (const char *s = getenv("RTB200_COUNT_STEPS"))
         ctx->count_steps = atoi(s) != 0;
+    if (const char *s = getenv("RTB200_FUSED"))
+        ctx->use_fused = atoi(s) != 0;
+    if (const char *s = getenv("RTB200_FLAT_MARCH"))
+        ctx->flat_march = atoi(s) != 0;
     *out = ctx;
     return RTB200_OK;
 }
@@ -431,6 +450,8 @@ void rtb200_destroy(rtb200_ctx *ctx)
     ctx->h_out.release();
     if (ctx->d_fail)
         cudaFree(ctx->d_fail);
+    if (ctx->d_work)
+        cudaFree(ctx->d_work);
     if (ctx->h_fail)
         cudaFreeHost(ctx->h_fail);
     for (auto e : ctx->ev)
@@ -622,7 +643,7 @@ int launch_list(rtb200_ctx *ctx, size_t n_rays, const Outputs &out_all, bool kee
         if (out.error)
             out.error += a;
         const size_t e0 = new_event(ctx, ctx->stream);
-        launch_march(P, c, true, h, ctx->d_fail, ctx->count_steps, ctx->stream);
+        launch_march(P, c, true, h, ctx->d_fail, ctx->count_steps, ctx->stream, ctx->d_work, ctx->flat_march);
         const size_t e1 = new_event(ctx, ctx->stream);
         launch_integrate_scatter(P, c, true, h, out, ctx->stream);
         const size_t e2 = new_event(ctx, ctx->stream);

@@ -16,7 +16,11 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include <algorithm>
+
+#include "rtb200_fp64.cuh"
 #include "rtb200_kernels.cuh"
+#include "rtb200_march_flat.cuh"
 
 namespace rtb {
 
@@ -207,13 +211,145 @@ __global__ void __launch_bounds__(128) march_kernel(const DevProblem P, const Ch
     }
 }
 
+// Persistent march: a fixed grid of warps pulls ray slots from a global counter.  Lane = ray,
+// flat state machine (rtb200_march_flat.cuh); a lane whose ray has finished immediately claims
+// the next unprocessed slot (one warp-aggregated atomic per refill), so lanes stay busy although
+// the number of steps per ray spans 1..~600 and more than half of the rays of ASE_medium leave
+// the plasma early.
+template <bool LIST, bool COUNT>
+__global__ void __launch_bounds__(128) march_flat_kernel(const DevProblem P, const Chunk c,
+                                                         const Handoff h, FailState *fail,
+                                                         unsigned long long *work)
+{
+    const int lane = threadIdx.x & 31;
+    const int S = (P.N - 1) * RTB_N_SUB;
+    const long long n_slots = LIST ? (c.ray1 - c.ray0) : (c.pix1 - c.pix0) * P.ab_max;
+    const bool use_emis = P.use_emis != 0;
+    FlatMarch m;
+    m.phase = PH_DONE;
+    m.steps = 0;
+    bool dead = false;
+    long long L = 0;
+    float rx = 0.f, ry = 0.f, ra = 0.f, rb = 0.f;
+    unsigned total_steps = 0;
+    GlobalSink sink{ h.seg };
+    for (;;) {
+        const bool need = m.phase == PH_DONE && !dead;
+        const unsigned want = __ballot_sync(0xffffffffu, need);
+        if (want != 0u) {
+            const int leader = __ffs(want) - 1;
+            unsigned long long first = 0;
+            if (lane == leader)
+                first = atomicAdd(work, (unsigned long long) __popc(want));
+            first = __shfl_sync(0xffffffffu, first, leader);
+            if (need) {
+                L = (long long) first + __popc(want & ((1u << lane) - 1u));
+                if (L >= n_slots) {
+                    dead = true;
+                } else {
+                    float ta, tb;
+                    bool active = true;
+                    if (LIST) {
+                        const float4 r = __ldg(&c.rays[c.ray0 + L]);
+                        const float2 t = __ldg(&c.tans[c.ray0 + L]);
+                        rx = r.x, ry = r.y, ra = r.z, rb = r.w, ta = t.x, tb = t.y;
+                    } else {
+                        const long long p = c.pix0 + L / P.ab_max;
+                        const int t = (int) (L % P.ab_max);
+                        const PixelRays pr = pixel_rays(P, p);
+                        active = t < pr.cnt;
+                        const int ab = pr.ab0 + t * (int) P.n_parallel;
+                        const int k = active ? ab / P.snb : 0, mm = active ? ab % P.snb : 0;
+                        rx = __ldg(&P.sxf[pr.i]);
+                        ry = __ldg(&P.syf[pr.j]);
+                        ra = __ldg(&P.saf[k]);
+                        rb = __ldg(&P.sbf[mm]);
+                        ta = __ldg(&P.tanA[k]);
+                        tb = __ldg(&P.tanB[mm]);
+                    }
+                    if (!active) {
+                        h.meta[L] = RTB_META_INACTIVE;
+                    } else {
+                        sink.seg = h.seg + L * S;
+                        flat_init(m, P.planes, P.N, P.method, P.dz0, rx, ry, ta, tb);
+                        if (m.phase == PH_DONE) // N == 1: nothing to march
+                            h.meta[L] = 0u;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, m.phase != PH_DONE) == 0u) {
+            if (__ballot_sync(0xffffffffu, !dead) == 0u)
+                break;
+            continue;
+        }
+        if (m.phase != PH_DONE) {
+            if (!flat_iterate(m, P.planes, P.N, P.method, P.dz0, P.c, use_emis, sink) ||
+                m.steps > (1u << 22)) {
+                m.phase = PH_DONE;
+                unsigned meta = (unsigned) m.seg_lo | ((unsigned) m.seg_hi << 12);
+                if (m.escaped)
+                    meta |= RTB_META_ESCAPED;
+                if (lt_0p01(fmul(m.s.z, m.s.z)) || m.steps > (1u << 22)) { // error -1 (:515-516)
+                    meta |= RTB_META_INVALID;
+                    report_failure(fail, 1, rx, ry, ra, rb);
+                } else if (h.exit_ray) {
+                    float4 e;
+                    e.x = m.pos.x;
+                    e.y = m.pos.y;
+                    e.z = fmul(atanf_fdlibm(fdiv(m.s.x, m.s.z)), 1e3f);
+                    e.w = fmul(atanf_fdlibm(fdiv(m.s.y, m.s.z)), 1e3f);
+                    h.exit_ray[L] = e;
+                }
+                h.meta[L] = meta;
+                total_steps += m.steps;
+            }
+        }
+    }
+    if (COUNT) {
+        unsigned tot = total_steps;
+        for (int o = 16; o > 0; o >>= 1)
+            tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (lane == 0)
+            atomicAdd(&fail->march_steps, (unsigned long long) tot);
+    }
+}
+
 void launch_march(const DevProblem &P, const Chunk &c, bool list_mode, const Handoff &h,
-                  FailState *fail, bool count_steps, cudaStream_t st)
+                  FailState *fail, bool count_steps, cudaStream_t st, unsigned long long *work,
+                  bool flat)
 {
     const long long n = list_mode ? (c.ray1 - c.ray0) : (c.pix1 - c.pix0) * P.ab_max;
     if (n <= 0)
         return;
     const int threads = 128;
+    if (flat) {
+        static int per_sm = 0, sms = 0;
+        if (per_sm == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, march_flat_kernel<false, false>,
+                                                          threads, 0);
+            if (per_sm < 1)
+                per_sm = 1;
+        }
+        long long blocks = (long long) sms * per_sm;
+        blocks = std::min(blocks, (n + threads - 1) / threads);
+        cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
+        if (list_mode) {
+            if (count_steps)
+                march_flat_kernel<true, true><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, fail, work);
+            else
+                march_flat_kernel<true, false><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, fail, work);
+        } else {
+            if (count_steps)
+                march_flat_kernel<false, true><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, fail, work);
+            else
+                march_flat_kernel<false, false><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, fail, work);
+        }
+        return;
+    }
     const unsigned blocks = (unsigned) ((n + threads - 1) / threads);
     if (list_mode) {
         if (count_steps)
@@ -232,9 +368,10 @@ void launch_march(const DevProblem &P, const Chunk &c, bool list_mode, const Han
 // frequency integration
 // ------------------------------------------------------------------------------------------
 
-// One (segment, sub-segment) update of one frequency bin with gain and spontaneous emission
-// (RayTraceImageHelper.h:549-557).  gl, el are float products widened to double.
-__device__ __forceinline__ double ase_update(double Iv, double gl, double el)
+// Library-precision form of one update (RayTraceImageHelper.h:549-557): only used for the
+// rare out-of-range arguments (|gl| >= 700, inf, NaN), where the library exp's overflow /
+// underflow / NaN semantics are wanted.
+__device__ __noinline__ double ase_update_library(double Iv, double gl, double el)
 {
     if (fabs(gl) < 1e-3) {
         return el * (1.0 + 0.5 * gl * (1.0 + 0.3333333333 * gl)) +
@@ -244,6 +381,22 @@ __device__ __forceinline__ double ase_update(double Iv, double gl, double el)
     return el / gl * (e - 1.0) + Iv * e;
 }
 
+__constant__ double c_exp_table[64] = { RTB_EXP_TABLE_VALUES };
+
+__device__ __forceinline__ void load_exp_table(double *T)
+{
+    for (int i = threadIdx.x; i < 64; i += blockDim.x)
+        T[i] = c_exp_table[i];
+    __syncthreads();
+}
+
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
     for (int o = 16; o > 0; o >>= 1)
@@ -251,14 +404,21 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// Integrates one ray's frequency bins k = lane + 32*q, q < KS, over its visited records.
+// Integrates one ray's frequency bins over its visited records.  Lane `lane` holds bins
+// k = kbase + lane + 32*q, q < KS; lanes past the last bin recompute bin K-1 (their results are
+// never stored), so the inner loop carries no lane predicate and the warp votes are exact.
 // Returns the failure code of the ray (0, 2 = negative, 3 = NaN), warp-uniform.
 template <int KS>
 __device__ __forceinline__ int integrate_ray(const DevProblem &P, const SegRec *seg, unsigned meta,
-                                             int lane, int kbase, double (&Iv)[KS])
+                                             int lane, int kbase, double (&Iv)[KS],
+                                             const double *T)
 {
     const int lo = meta & 0xfff, hi = (meta >> 12) & 0xfff;
     const int K = P.K;
+    int koff[KS];
+#pragma unroll
+    for (int q = 0; q < KS; q++)
+        koff[q] = min(kbase + lane + 32 * q, K - 1);
     if (P.use_emis) {
         for (int pl = lo / RTB_N_SUB; pl < P.N - 1; pl++) {
             const float *gvp = P.planes[pl + 1].gv;
@@ -270,15 +430,29 @@ __device__ __forceinline__ int integrate_ray(const DevProblem &P, const SegRec *
                 const float gvl = __int_as_float(rv.x), evl = __int_as_float(rv.y);
                 if (gvl == 0.0f && evl == 0.0f)
                     continue; // gl = el = 0: the update is the identity
-                const float *row = gvp + (size_t) rv.z * K + kbase;
+                const float *row = gvp + (size_t) rv.z * K;
+                float g[KS];
+#pragma unroll
+                for (int q = 0; q < KS; q++)
+                    g[q] = __ldg(row + koff[q]);
 #pragma unroll
                 for (int q = 0; q < KS; q++) {
-                    const int k = lane + 32 * q;
-                    if (kbase + k < K) {
-                        const float g = __ldg(row + k);
-                        const double gl = (double) __fmul_rn(gvl, g);
-                        const double el = (double) __fmul_rn(evl, g);
-                        Iv[q] = ase_update(Iv[q], gl, el);
+                    const float glf = __fmul_rn(gvl, g[q]);
+                    const float elf = __fmul_rn(evl, g[q]);
+                    const float ag = fabsf(glf);
+                    const bool small = ag < 1e-3f; // == (fabs((double) glf) < 1e-3)
+                    const unsigned b_small = __ballot_sync(0xffffffffu, small);
+                    const unsigned b_odd = __ballot_sync(0xffffffffu, !(ag < 700.0f));
+                    const double gl = (double) glf, el = (double) elf;
+                    if (b_odd != 0u) { // some lane has |gl| >= 700, inf or NaN: library semantics
+                        Iv[q] = ase_update_library(Iv[q], gl, el);
+                    } else {
+                        double a = 0.0, b = 0.0;
+                        if (b_small != 0u) // warp-uniform: some lane takes the Taylor branch
+                            a = ase_update_small(Iv[q], gl, el);
+                        if (b_small != 0xffffffffu) // warp-uniform: some lane takes the exp branch
+                            b = ase_update_large(Iv[q], gl, el, rcp_approx(glf), T);
+                        Iv[q] = small ? a : b;
                     }
                 }
             }
@@ -297,18 +471,15 @@ __device__ __forceinline__ int integrate_ray(const DevProblem &P, const SegRec *
                     continue;
                 const int4 rv = __ldg(reinterpret_cast<const int4 *>(&seg[s]));
                 const double gvl = (double) __int_as_float(rv.x);
-                const float *row = gvp + (size_t) rv.z * K + kbase;
+                const float *row = gvp + (size_t) rv.z * K;
 #pragma unroll
-                for (int q = 0; q < KS; q++) {
-                    const int k = lane + 32 * q;
-                    if (kbase + k < K)
-                        gl[q] = __dadd_rn(gl[q], __dmul_rn(gvl, (double) __ldg(row + k)));
-                }
+                for (int q = 0; q < KS; q++)
+                    gl[q] = __dadd_rn(gl[q], __dmul_rn(gvl, (double) __ldg(row + koff[q])));
             }
         }
 #pragma unroll
         for (int q = 0; q < KS; q++)
-            Iv[q] *= exp(gl[q]);
+            Iv[q] *= exp_any(gl[q], T);
     }
     bool neg = false, nan = false;
 #pragma unroll
@@ -328,6 +499,8 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32)
     integrate_ase_owner_kernel(const DevProblem P, const Chunk c, const Handoff h, const Outputs o)
 {
     __shared__ double part[RTB_OWNER_WARPS][KS * 32];
+    __shared__ double exp_tab[64];
+    load_exp_table(exp_tab);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long p = c.pix0 + blockIdx.x;
     const PixelRays pr = pixel_rays(P, p);
@@ -350,7 +523,7 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32)
 #pragma unroll
         for (int q = 0; q < KS; q++)
             Iv[q] = 0.0;
-        const int code = integrate_ray<KS>(P, h.seg + slot * S, meta, lane, 0, Iv);
+        const int code = integrate_ray<KS>(P, h.seg + slot * S, meta, lane, 0, Iv, exp_tab);
         const int ab = pr.ab0 + t * (int) P.n_parallel;
         const int ka = ab / P.snb, m = ab % P.snb;
         if (code != 0) {
@@ -402,6 +575,247 @@ void launch_integrate_ase_owner(const DevProblem &P, const Chunk &c, const Hando
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused ASE kernel: march + frequency integration + binning in ONE launch, no global hand-off.
+//
+// One CTA per source pixel.  Each warp repeatedly claims a batch of RB rays of the pixel and
+//   (1) marches them, lane = ray, flat state machine (rtb200_march_flat.cuh) with refill: a
+//       lane whose ray has finished (58% of ASE_medium's rays escape early) immediately takes
+//       the next ray of the batch, so lanes stay busy until the batch is exhausted;
+//       gvl / evl / ivl go to the warp's private shared-memory slab [record][ray];
+//   (2) integrates them, lane = frequency bin, one ray after the other, reading the records
+//       back as shared-memory broadcasts and the lineshape rows gv[cell][k] as coalesced
+//       read-only loads; the pixel spectrum accumulates in registers, I_ang through a
+//       warp-shuffle reduction and one FP64 atomic per ray.
+// Warps of one SM are in different phases at any time, so the FP32/XU-heavy march and the
+// FP64-heavy integration overlap on the SM's pipes.
+// ------------------------------------------------------------------------------------------
+struct SmemSink {
+    float *gvl, *evl;
+    int *cell;
+    int rb, slot;
+    __device__ __forceinline__ void operator()(int idx, float g, float e, int c) const
+    {
+        gvl[idx * rb + slot] = g;
+        evl[idx * rb + slot] = e;
+        cell[idx * rb + slot] = c;
+    }
+};
+
+#define RTB_FUSED_WARPS 8
+
+template <int KS>
+__global__ void __launch_bounds__(RTB_FUSED_WARPS * 32, 2)
+    trace_ase_fused_kernel(const DevProblem P, const long long pix0, const int RB, const Outputs o)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double part[RTB_FUSED_WARPS][KS * 32];
+    __shared__ double exp_tab[64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int S = (P.N - 1) * RTB_N_SUB;
+    const int K = P.K;
+    // dynamic shared memory: gv row pointers of the planes, then one slab per warp
+    const float **s_gv = reinterpret_cast<const float **>(smem_raw);
+    const size_t slab_words = (size_t) RB * (3 * S + 1);
+    float *slab = reinterpret_cast<float *>(smem_raw + ((sizeof(float *) * P.N + 15) & ~size_t(15))) +
+                  (size_t) warp * slab_words;
+    float *s_gvl = slab, *s_evl = slab + (size_t) RB * S;
+    int *s_cell = reinterpret_cast<int *>(slab + (size_t) 2 * RB * S);
+    unsigned *s_meta = reinterpret_cast<unsigned *>(slab + (size_t) 3 * RB * S);
+    for (int i = threadIdx.x; i < P.N; i += blockDim.x)
+        s_gv[i] = P.planes[i].gv;
+    load_exp_table(exp_tab); // includes __syncthreads()
+
+    const long long p = pix0 + blockIdx.x;
+    const PixelRays pr = pixel_rays(P, p);
+    const float rx = __ldg(&P.sxf[pr.i]), ry = __ldg(&P.syf[pr.j]);
+    const bool use_emis = P.use_emis != 0;
+    double pix[KS], dv2[KS];
+    int koff[KS];
+#pragma unroll
+    for (int q = 0; q < KS; q++) {
+        pix[q] = 0.0;
+        const int k = lane + 32 * q;
+        dv2[q] = k < K ? __ldg(&P.dv2[k]) : 0.0;
+        koff[q] = min(k, K - 1);
+    }
+
+    // Batches are assigned to warps statically (b = warp, warp + 8, ...) so that the order in
+    // which a pixel's rays are summed, and therefore the image, is bit-reproducible.
+    for (int b = warp;; b += RTB_FUSED_WARPS) {
+        const int base = b * RB;
+        if (base >= pr.cnt)
+            break;
+        const int nb = min(RB, pr.cnt - base);
+
+        // ================= (1) march: lane = ray, refill from the batch =================
+        {
+            FlatMarch m;
+            m.phase = PH_DONE;
+            SmemSink sink{ s_gvl, s_evl, s_cell, RB, 0 };
+            int next = 0; // warp-uniform: first unclaimed ray of the batch
+            int ka = 0, kb = 0;
+            for (unsigned trip = 0; trip < (1u << 24); ++trip) {
+                const bool need = m.phase == PH_DONE;
+                const unsigned want = __ballot_sync(0xffffffffu, need);
+                if (want != 0u && next < nb) {
+                    if (need) {
+                        const int idx = next + __popc(want & ((1u << lane) - 1u));
+                        if (idx < nb) {
+                            sink.slot = idx;
+                            const int ab = pr.ab0 + (base + idx) * (int) P.n_parallel;
+                            ka = ab / P.snb;
+                            kb = ab % P.snb;
+                            flat_init(m, P.planes, P.N, 1, P.dz0, rx, ry, __ldg(&P.tanA[ka]),
+                                      __ldg(&P.tanB[kb]));
+                        }
+                    }
+                    next += __popc(want);
+                }
+                if (__ballot_sync(0xffffffffu, m.phase != PH_DONE) == 0u)
+                    break;
+                if (m.phase != PH_DONE) {
+                    if (!flat_iterate(m, P.planes, P.N, 1, P.dz0, P.c, use_emis, sink)) {
+                        unsigned meta = (unsigned) m.seg_lo | ((unsigned) m.seg_hi << 12);
+                        if (m.escaped)
+                            meta |= RTB_META_ESCAPED;
+                        if (lt_0p01(fmul(m.s.z, m.s.z))) { // error -1 (:515-516)
+                            meta |= RTB_META_INVALID;
+                            report_failure(o.fail, 1, rx, ry, __ldg(&P.saf[ka]), __ldg(&P.sbf[kb]));
+                        }
+                        s_meta[sink.slot] = meta;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+
+        // ================= (2) integrate: lane = frequency bin, ray after ray =================
+        for (int r = 0; r < nb; r++) {
+            const unsigned meta = s_meta[r];
+            if (meta & RTB_META_INVALID)
+                continue;
+            const int lo = meta & 0xfff, hi = (meta >> 12) & 0xfff;
+            double Iv[KS];
+#pragma unroll
+            for (int q = 0; q < KS; q++)
+                Iv[q] = 0.0;
+            for (int sgm = lo; sgm < hi; sgm++) {
+                const float gvl = s_gvl[sgm * RB + r], evl = s_evl[sgm * RB + r];
+                if (gvl == 0.0f && evl == 0.0f)
+                    continue; // gl = el = 0: the update is the identity
+                const float *row = s_gv[sgm / RTB_N_SUB + 1] + (size_t) s_cell[sgm * RB + r] * K;
+                float g[KS];
+#pragma unroll
+                for (int q = 0; q < KS; q++)
+                    g[q] = __ldg(row + koff[q]);
+#pragma unroll
+                for (int q = 0; q < KS; q++) {
+                    const float glf = __fmul_rn(gvl, g[q]);
+                    const float elf = __fmul_rn(evl, g[q]);
+                    const float ag = fabsf(glf);
+                    const bool small = ag < 1e-3f; // == (fabs((double) glf) < 1e-3)
+                    const unsigned b_small = __ballot_sync(0xffffffffu, small);
+                    const unsigned b_odd = __ballot_sync(0xffffffffu, !(ag < 700.0f));
+                    const double gl = (double) glf, el = (double) elf;
+                    if (b_odd != 0u) {
+                        Iv[q] = ase_update_library(Iv[q], gl, el);
+                    } else {
+                        double a = 0.0, bb = 0.0;
+                        if (b_small != 0u)
+                            a = ase_update_small(Iv[q], gl, el);
+                        if (b_small != 0xffffffffu)
+                            bb = ase_update_large(Iv[q], gl, el, rcp_approx(glf), exp_tab);
+                        Iv[q] = small ? a : bb;
+                    }
+                }
+            }
+            bool neg = false, nan = false;
+#pragma unroll
+            for (int q = 0; q < KS; q++) {
+                neg = neg || Iv[q] < 0.0;
+                nan = nan || Iv[q] != Iv[q];
+            }
+            const bool any_neg = __any_sync(0xffffffffu, neg);
+            const bool any_nan = __any_sync(0xffffffffu, nan);
+            const int ab = pr.ab0 + (base + r) * (int) P.n_parallel;
+            const int ka = ab / P.snb, kb = ab % P.snb;
+            if (any_neg || any_nan) {
+                if (lane == 0)
+                    report_failure(o.fail, any_neg ? 2 : 3, rx, ry, P.saf[ka], P.sbf[kb]);
+                continue;
+            }
+            double w = 0.0;
+#pragma unroll
+            for (int q = 0; q < KS; q++) {
+                w += dv2[q] * Iv[q];
+                pix[q] += Iv[q] * P.scale;
+            }
+            w = warp_sum(w);
+            const int ba = __ldg(&P.binA[ka]), bb = __ldg(&P.binB[kb]);
+            if (lane == 0 && ba >= 0 && bb >= 0)
+                atomicAdd(&o.I_ang[ba + bb * P.na], w);
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int q = 0; q < KS; q++)
+        part[warp][q * 32 + lane] = pix[q];
+    __syncthreads();
+    const int pi = __ldg(&P.pixI[pr.i]), pj = __ldg(&P.pixJ[pr.j]);
+    if (pi < 0 || pj < 0)
+        return;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < RTB_FUSED_WARPS; w++)
+            sum += part[w][k];
+        o.image[(size_t) K * ((size_t) pi + (size_t) pj * P.nx) + k] = sum;
+    }
+}
+
+size_t fused_smem_bytes(const DevProblem &P, int RB)
+{
+    const int S = (P.N - 1) * RTB_N_SUB;
+    return ((sizeof(float *) * P.N + 15) & ~size_t(15)) +
+           (size_t) RTB_FUSED_WARPS * RB * (3 * S + 1) * sizeof(float);
+}
+
+// Returns false when the problem does not fit the fused kernel (K > 128 or the per-warp slabs
+// exceed shared memory): the caller then uses the two-kernel path.
+bool launch_trace_ase_fused(const DevProblem &P, long long pix0, long long pix1, const Outputs &o,
+                            cudaStream_t st)
+{
+    const long long npix = pix1 - pix0;
+    if (npix <= 0)
+        return true;
+    const int ks = (P.K + 31) / 32;
+    if (ks > 4 || P.N < 2)
+        return false;
+    int RB = 64;
+    if (fused_smem_bytes(P, RB) > 100 * 1024)
+        RB = 32;
+    const size_t smem = fused_smem_bytes(P, RB);
+    if (smem > 200 * 1024)
+        return false;
+    const unsigned blocks = (unsigned) npix;
+    const int threads = RTB_FUSED_WARPS * 32;
+#define RTB_LAUNCH_FUSED(KS_)                                                                   \
+    do {                                                                                        \
+        cudaFuncSetAttribute(trace_ase_fused_kernel<KS_>,                                       \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);          \
+        trace_ase_fused_kernel<KS_><<<blocks, threads, smem, st>>>(P, pix0, RB, o);             \
+    } while (0)
+    switch (ks) {
+    case 1: RTB_LAUNCH_FUSED(1); break;
+    case 2: RTB_LAUNCH_FUSED(2); break;
+    case 3: RTB_LAUNCH_FUSED(3); break;
+    default: RTB_LAUNCH_FUSED(4); break;
+    }
+#undef RTB_LAUNCH_FUSED
+    return true;
+}
+
 // getIndex (RayTraceImageCPU.cpp:11-16) on the device, for the exit ray.
 __device__ __forceinline__ int dev_get_index(int n, const double *x, double dx, double y)
 {
@@ -430,6 +844,8 @@ __global__ void __launch_bounds__(256)
     integrate_scatter_kernel(const DevProblem P, const Chunk c, const Handoff h, const Outputs o)
 {
     constexpr int KS = 2;
+    __shared__ double exp_tab[64];
+    load_exp_table(exp_tab);
     const int lane = threadIdx.x & 31;
     const long long warp_id = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long) gridDim.x * blockDim.x) >> 5;
@@ -495,7 +911,7 @@ __global__ void __launch_bounds__(256)
                 Iv[q] = (f != 0.0 && k < K) ? __dmul_rn(f, __ldg(&P.seed_fv[k])) : 0.0;
             }
             if (!invalid) {
-                const int cc = integrate_ray<KS>(P, h.seg + slot * S, meta, lane, kbase, Iv);
+                const int cc = integrate_ray<KS>(P, h.seg + slot * S, meta, lane, kbase, Iv, exp_tab);
                 if (cc != 0) {
                     code = code == 0 ? cc : (cc < code ? cc : code); // negative (2) wins over NaN (3)
                 }
@@ -534,7 +950,7 @@ __global__ void __launch_bounds__(256)
                     const int k = kbase + lane + 32 * q;
                     Iv[q] = (f != 0.0 && k < K) ? __dmul_rn(f, __ldg(&P.seed_fv[k])) : 0.0;
                 }
-                integrate_ray<KS>(P, h.seg + slot * S, meta, lane, kbase, Iv);
+                integrate_ray<KS>(P, h.seg + slot * S, meta, lane, kbase, Iv, exp_tab);
 #pragma unroll
                 for (int q = 0; q < KS; q++) {
                     const int k = kbase + lane + 32 * q;

@@ -31,8 +31,11 @@ struct Outputs {
     FailState *fail; // never null
 };
 
+// flat = true: persistent flat-state-machine march with refill (work = device counter, reset by
+// the launcher); flat = false: the literal nested form, one thread per ray.
 void launch_march(const DevProblem &P, const Chunk &c, bool list_mode, const Handoff &h,
-                  FailState *fail, bool count_steps, cudaStream_t st);
+                  FailState *fail, bool count_steps, cudaStream_t st, unsigned long long *work,
+                  bool flat);
 // ASE (method 1, emission + gain), grid mode: one CTA per source pixel, the pixel's spectrum is
 // owned by the CTA (plain stores), I_ang by atomics.
 void launch_integrate_ase_owner(const DevProblem &P, const Chunk &c, const Handoff &h,
@@ -41,6 +44,10 @@ void launch_integrate_ase_owner(const DevProblem &P, const Chunk &c, const Hando
 // non-identity owner maps) and/or per-ray dumps.
 void launch_integrate_scatter(const DevProblem &P, const Chunk &c, bool list_mode,
                               const Handoff &h, const Outputs &o, cudaStream_t st);
+// Fused ASE path (march + integration + binning in one launch, shared-memory hand-off).
+// Returns false when the problem does not fit it; the caller falls back to the kernels above.
+bool launch_trace_ase_fused(const DevProblem &P, long long pix0, long long pix1, const Outputs &o,
+                            cudaStream_t st);
 void launch_fp64_peak(double *out, int iters, cudaStream_t st, int *blocks, int *threads);
 
 } // namespace rtb

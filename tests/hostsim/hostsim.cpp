@@ -9,6 +9,8 @@
 #include <cstring>
 #include <vector>
 
+#include "../../raytrace-miniapp_b200/csrc/rtb200_fp64.cuh"
+#include "../../raytrace-miniapp_b200/csrc/rtb200_march_flat.cuh"
 #include "../../raytrace-miniapp_b200/csrc/rtb200_pack.h"
 
 using namespace rtb;
@@ -33,7 +35,7 @@ extern "C" {
 // [count][(N-1)*3] (zero outside the visited range), exit [count][6] = pos.x, pos.y, s.x, s.y,
 // s.z, escaped; meta [count][2] = seg_lo, seg_hi.  Returns total march steps, or -1.
 long long hostsim_march(const rtb200_problem *p, long long first, long long count, float *gvl,
-                        float *evl, int *ivl, float *exit_state, int *meta)
+                        float *evl, int *ivl, float *exit_state, int *meta, int flat)
 {
     DevProblem P;
     const size_t bytes = pack_problem(*p, false, 0, 0.0, nullptr, nullptr, P);
@@ -57,8 +59,22 @@ long long hostsim_march(const rtb200_problem *p, long long first, long long coun
         ArraySink sink{ gvl + r * S, evl + r * S, ivl + r * S };
         MarchResult res;
         unsigned steps = 0;
-        march_ray(P.planes, P.N, P.method, P.dz0, P.c, P.use_emis != 0, P.sxf[i], P.syf[j],
-                  P.tanA[k], P.tanB[m], sink, res, steps);
+        if (flat) { // the flat state machine the fused GPU kernel runs
+            FlatMarch fm;
+            flat_init(fm, P.planes, P.N, P.method, P.dz0, P.sxf[i], P.syf[j], P.tanA[k], P.tanB[m]);
+            while (fm.phase != PH_DONE &&
+                   flat_iterate(fm, P.planes, P.N, P.method, P.dz0, P.c, P.use_emis != 0, sink)) {
+            }
+            res.pos = fm.pos;
+            res.s = fm.s;
+            res.escaped = fm.escaped;
+            res.seg_lo = fm.seg_lo;
+            res.seg_hi = fm.seg_hi;
+            steps = fm.steps;
+        } else {
+            march_ray(P.planes, P.N, P.method, P.dz0, P.c, P.use_emis != 0, P.sxf[i], P.syf[j],
+                      P.tanA[k], P.tanB[m], sink, res, steps);
+        }
         steps_total += steps;
         float *e = exit_state + r * 6;
         e[0] = res.pos.x;
@@ -107,6 +123,25 @@ int hostsim_find_cell(const double *X, int n, double Y)
     double xl, xr;
     const double inv = n > 1 ? (double) (n - 1) / (X[n - 1] - X[0]) : 0.0;
     return find_cell(X, n, X[0], inv, Y, xl, xr);
+}
+
+// FP64 update doors (rtb200_fp64.cuh): the fast exp and the two update branches.
+static const double k_exp_table[64] = { RTB_EXP_TABLE_VALUES };
+void hostsim_exp(const double *x, double *y, int n)
+{
+    for (int i = 0; i < n; i++)
+        y[i] = exp_any(x[i], k_exp_table);
+}
+// One update with float inputs gvl, evl, g as the kernel forms them; branch chosen like the kernel.
+double hostsim_ase_update(double Iv, float gvl, float evl, float g)
+{
+    const float glf = gvl * g, elf = evl * g;
+    const double gl = (double) glf, el = (double) elf;
+    if (!(fabsf(glf) < 700.0f))
+        return -1.0; // library path on the device
+    if (fabsf(glf) < 1e-3f)
+        return ase_update_small(Iv, gl, el);
+    return ase_update_large(Iv, gl, el, 1.0f / glf, k_exp_table);
 }
 
 } // extern "C"

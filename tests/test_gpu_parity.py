@@ -63,7 +63,7 @@ def test_ase_small_image_vs_oracle_and_reference(ase_small, oracle, ctx):
     g0, g1 = np.linalg.norm(extra["dat_golden_image"]), np.linalg.norm(img)
     assert (g0 - g1) / g0 <= 5e-6
     t = ctx.timings()
-    assert t["kernel_launches"] >= 2 and t["march_ms"] > 0 and t["integrate_ms"] > 0
+    assert t["kernel_launches"] >= 1 and t["march_ms"] + t["integrate_ms"] > 0
 
 
 def test_seed_small_image_vs_reference(seed_small, ctx):

@@ -22,7 +22,7 @@ def hostsim():
                    check=True)
     L = C.CDLL(so)
     L.hostsim_march.restype = C.c_longlong
-    L.hostsim_march.argtypes = [C.POINTER(abi.CProblem), C.c_longlong, C.c_longlong] + [C.c_void_p] * 5
+    L.hostsim_march.argtypes = [C.POINTER(abi.CProblem), C.c_longlong, C.c_longlong] + [C.c_void_p] * 5 + [C.c_int]
     L.hostsim_pchip.restype = C.c_double
     L.hostsim_pchip.argtypes = [C.c_size_t, abi.c_double_p, abi.c_double_p, C.c_double]
     L.hostsim_get_index.argtypes = [C.c_int, abi.c_double_p, C.c_double, C.c_double]
@@ -31,22 +31,25 @@ def hostsim():
     return L
 
 
-def _march(L, p):
+def _march(L, p, flat=0):
     n, S = p.n_rays, (p.N - 1) * 3
     cp, keep = p.c_struct()
     gvl, evl = np.zeros((n, S), np.float32), np.zeros((n, S), np.float32)
     ivl, ex, meta = np.zeros((n, S), np.int32), np.zeros((n, 6), np.float32), np.zeros((n, 2), np.int32)
     steps = L.hostsim_march(C.byref(cp), 0, n, gvl.ctypes.data, evl.ctypes.data, ivl.ctypes.data,
-                            ex.ctypes.data, meta.ctypes.data)
+                            ex.ctypes.data, meta.ctypes.data, flat)
     return gvl, evl, ivl, ex, meta, steps
 
 
+@pytest.mark.parametrize("flat", [0, 1], ids=["nested", "flat"])
 @pytest.mark.parametrize("name,stride,start", [("ase_small", 41, 3), ("seed_small", 1999, 11)])
-def test_march_bit_identical_to_oracle(name, stride, start, request, oracle, hostsim):
+def test_march_bit_identical_to_oracle(name, stride, start, flat, request, oracle, hostsim):
+    """flat=0: the literal nested form (rtb200_march.cuh); flat=1: the flat state machine of
+    the fused kernel (rtb200_march_flat.cuh).  Both must reproduce the oracle bit for bit."""
     p, _ = request.getfixturevalue(name)
     p.N_start, p.N_parallel = start, stride
     try:
-        gvl, evl, ivl, ex, meta, steps = _march(hostsim, p)
+        gvl, evl, ivl, ex, meta, steps = _march(hostsim, p, flat)
         o = oracle.calc_rays(p, p.rays())
     finally:
         p.N_start, p.N_parallel = 0, 1
