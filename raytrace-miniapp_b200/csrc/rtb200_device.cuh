@@ -2,6 +2,7 @@
 // kernels.  Everything the kernels read lives in ONE packed blob (rtb200_pack.h) uploaded with a
 // single H2D copy; the structs below hold pointers into it.
 #pragma once
+#include "rtb200_fp64.cuh"
 #include "rtb200_march.cuh"
 
 namespace rtb {
@@ -57,6 +58,9 @@ struct DevProblem {
     //     coordinate is outside the seed grid (calc_seed_inline's range test, :235-237)
     const double *seed_fx, *seed_fy, *seed_fa, *seed_fb, *seed_fv;
     double seed_f0;
+    // --- constants of the FP64 update (rtb200_fp64.cuh), kept in the kernel parameter bank
+    double kfp[RTB_K_COUNT];
+    const double *kfp_g; // the same constants in the staged blob (read once with volatile loads)
 };
 
 } // namespace rtb

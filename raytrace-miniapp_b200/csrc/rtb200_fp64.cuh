@@ -20,8 +20,9 @@ namespace rtb {
 
 #define RTB_EXP_MAGIC 6755399441055744.0 /* 1.5 * 2^52: round-to-nearest-integer by addition */
 
-// Constants of the update.  On the device they are read as constant-bank operands (no
-// per-use materialisation of 64-bit immediates); the host build uses the same values.
+// Constants of the update, as an array so that the kernels can keep them in the kernel
+// PARAMETER bank (DevProblem::kfp): c[0x0][..] is directly addressable as an FP64 operand,
+// which avoids materialising 64-bit immediates (2 UMOV per use) or LDC loads in the hot loop.
 #define RTB_K_64_OVER_LN2 0
 #define RTB_K_LN2_64_HI 1
 #define RTB_K_LN2_64_LO 2
@@ -29,18 +30,10 @@ namespace rtb {
 #define RTB_K_C4 4
 #define RTB_K_C3 5
 #define RTB_K_THIRD 6
+#define RTB_K_COUNT 8
 #define RTB_K_VALUES                                                                             \
     RTB_EXP_64_OVER_LN2, -RTB_EXP_LN2_64_HI, -RTB_EXP_LN2_64_LO, 1.0 / 120.0, 1.0 / 24.0,        \
         1.0 / 6.0, 0.3333333333, 0.0
-#if defined(__CUDACC__)
-__constant__ double c_fp64_k[8] = { RTB_K_VALUES };
-#endif
-#if defined(__CUDA_ARCH__)
-#define RTB_K(i) c_fp64_k[i]
-#else
-static const double h_fp64_k[8] = { RTB_K_VALUES };
-#define RTB_K(i) h_fp64_k[i]
-#endif
 
 RTB_HD double fma64(double a, double b, double c)
 {
@@ -75,48 +68,70 @@ RTB_HD double scale_pow2(double e, int m) // e * 2^m for a normal e and a normal
 #endif
 }
 
-// exp(x) for |x| < 700 (the caller routes everything else to the library exp).
-// T: 64-entry table of 2^(j/64) (shared memory on the device).
-RTB_HD double exp_core(double x, const double *T)
+// The constants and the 2^(j/64) table are reached through a provider type so that the same
+// arithmetic runs with plain arrays on the host (tests/hostsim) and, in the hot kernel, with
+// the constants pinned in registers and the table read by explicit shared-memory loads.
+struct ArrayConsts {
+    const double *kc; // RTB_K_VALUES
+    const double *T;  // 2^(j/64), j = 0..63
+    RTB_HD double l2e() const { return kc[RTB_K_64_OVER_LN2]; }
+    RTB_HD double hi() const { return kc[RTB_K_LN2_64_HI]; }
+    RTB_HD double lo() const { return kc[RTB_K_LN2_64_LO]; }
+    RTB_HD double c5() const { return kc[RTB_K_C5]; }
+    RTB_HD double c4() const { return kc[RTB_K_C4]; }
+    RTB_HD double c3() const { return kc[RTB_K_C3]; }
+    RTB_HD double third() const { return kc[RTB_K_THIRD]; }
+    RTB_HD double tab(int j) const { return T[j]; }
+};
+
+// exp(x) for |x| < 700 (the caller routes everything else to the library exp).  The range
+// reduction uses ln2/64 split in two parts: accurate to ~2e-16 over the whole range.
+template <class KC>
+RTB_HD double exp_core(double x, const KC &C)
 {
-    const double t = fma64(x, RTB_K(RTB_K_64_OVER_LN2), RTB_EXP_MAGIC);
+    const double t = fma64(x, C.l2e(), RTB_EXP_MAGIC);
     const int n = lo32(t);
     const double tn = t - RTB_EXP_MAGIC;
-    double r = fma64(tn, RTB_K(RTB_K_LN2_64_HI), x);
-    r = fma64(tn, RTB_K(RTB_K_LN2_64_LO), r);
-    double q = fma64(r, RTB_K(RTB_K_C5), RTB_K(RTB_K_C4));
-    q = fma64(r, q, RTB_K(RTB_K_C3));
+    double r = fma64(tn, C.hi(), x);
+    r = fma64(tn, C.lo(), r);
+    double q = fma64(r, C.c5(), C.c4());
+    q = fma64(r, q, C.c3());
     q = fma64(r, q, 0.5);
     q = fma64(r, q, 1.0);
-    const double Tj = T[n & 63];
+    const double Tj = C.tab(n & 63);
     const double e = fma64(Tj, r * q, Tj);
     return scale_pow2(e, n >> 6);
 }
 
-RTB_HD double exp_any(double x, const double *T)
+template <class KC>
+RTB_HD double exp_any(double x, const KC &C)
 {
     if (fabs(x) < 700.0)
-        return exp_core(x, T);
+        return exp_core(x, C);
     return exp(x); // overflow / underflow / NaN: the library routine's semantics
 }
 
-// The |gl| < 1e-3 branch.
-RTB_HD double ase_update_small(double Iv, double gl, double el)
+// The |gl| < 1e-3 branch (7 FP64 instructions).
+template <class KC>
+RTB_HD double ase_update_small(double Iv, double gl, double el, const KC &C)
 {
-    const double a = fma64(gl, RTB_K(RTB_K_THIRD), 1.0);
+    const double a = fma64(gl, C.third(), 1.0);
     const double c = fma64(0.5 * gl, a, 1.0);
     const double d = fma64(gl, 0.5, 1.0);
     const double e = fma64(gl, d, 1.0);
     return fma64(el, c, Iv * e);
 }
 
-// The exp branch for |gl| < 700; rcp_seed is a single-precision approximation of 1/gl.
-RTB_HD double ase_update_large(double Iv, double gl, double el, float rcp_seed, const double *T)
+// The exp branch for |gl| < 700 (15 FP64 instructions); rcp_seed is a single-precision
+// approximation of 1/gl.  el/gl*(e - 1) + Iv*e is evaluated as u*e + (Iv*e - u), u = el/gl.
+template <class KC>
+RTB_HD double ase_update_large(double Iv, double gl, double el, float rcp_seed, const KC &C)
 {
-    const double e = exp_core(gl, T);
+    const double e = exp_core(gl, C);
     const double r0 = (double) rcp_seed;
     const double r1 = fma64(r0, fma64(-gl, r0, 1.0), r0); // 1/gl to ~2^-46
-    return fma64(el * r1, e - 1.0, Iv * e);
+    const double u = el * r1;
+    return fma64(u, e, fma64(Iv, e, -u));
 }
 
 } // namespace rtb

@@ -415,6 +415,7 @@ __device__ __forceinline__ int integrate_ray(const DevProblem &P, const SegRec *
 {
     const int lo = meta & 0xfff, hi = (meta >> 12) & 0xfff;
     const int K = P.K;
+    const ArrayConsts KC{ P.kfp, T };
     int koff[KS];
 #pragma unroll
     for (int q = 0; q < KS; q++)
@@ -449,9 +450,9 @@ __device__ __forceinline__ int integrate_ray(const DevProblem &P, const SegRec *
                     } else {
                         double a = 0.0, b = 0.0;
                         if (b_small != 0u) // warp-uniform: some lane takes the Taylor branch
-                            a = ase_update_small(Iv[q], gl, el);
+                            a = ase_update_small(Iv[q], gl, el, KC);
                         if (b_small != 0xffffffffu) // warp-uniform: some lane takes the exp branch
-                            b = ase_update_large(Iv[q], gl, el, rcp_approx(glf), T);
+                            b = ase_update_large(Iv[q], gl, el, rcp_approx(glf), KC);
                         Iv[q] = small ? a : b;
                     }
                 }
@@ -479,7 +480,128 @@ __device__ __forceinline__ int integrate_ray(const DevProblem &P, const SegRec *
         }
 #pragma unroll
         for (int q = 0; q < KS; q++)
-            Iv[q] *= exp_any(gl[q], T);
+            Iv[q] *= exp_any(gl[q], KC);
+    }
+    bool neg = false, nan = false;
+#pragma unroll
+    for (int q = 0; q < KS; q++) {
+        neg = neg || Iv[q] < 0.0;
+        nan = nan || Iv[q] != Iv[q];
+    }
+    const bool any_neg = __any_sync(0xffffffffu, neg);
+    const bool any_nan = __any_sync(0xffffffffu, nan);
+    return any_neg ? 2 : (any_nan ? 3 : 0);
+}
+
+// Hot-path ray integrator of the owner kernel (ASE mode, one pass over K <= 32*KS bins).
+//  * the ray's records are fetched with ONE coalesced 16-byte load per 32 records (lane j holds
+//    record c0 + j) and handed out by warp shuffles, instead of one dependent global load per
+//    record;
+//  * the lineshape row of record j+1 is requested before record j is integrated;
+//  * the gv base pointers of the planes come from a shared-memory table.
+// Constants of the update pinned in registers for the lifetime of the kernel: they are read
+// once from the staged blob with VOLATILE loads, so neither the compiler nor ptxas can
+// rematerialise them inside the loop as pairs of 32-bit immediates or constant-bank reloads
+// (measured: ~30 of 150 instructions per record were such reloads, profiles/r01).  The exp
+// table is addressed by an explicit shared-memory load.
+struct PinnedConsts {
+    double l2e_, hi_, lo_, c5_, c4_, c3_, third_;
+    unsigned tab_; // shared-space address of the 2^(j/64) table
+    __device__ __forceinline__ static double pin(const double *p)
+    {
+        double x;
+        asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(x) : "l"(p));
+        return x;
+    }
+    __device__ __forceinline__ PinnedConsts(const double *kc, const double *T)
+    {
+        l2e_ = pin(kc + RTB_K_64_OVER_LN2);
+        hi_ = pin(kc + RTB_K_LN2_64_HI);
+        lo_ = pin(kc + RTB_K_LN2_64_LO);
+        c5_ = pin(kc + RTB_K_C5);
+        c4_ = pin(kc + RTB_K_C4);
+        c3_ = pin(kc + RTB_K_C3);
+        third_ = pin(kc + RTB_K_THIRD);
+        tab_ = (unsigned) __cvta_generic_to_shared(T);
+    }
+    __device__ __forceinline__ double l2e() const { return l2e_; }
+    __device__ __forceinline__ double hi() const { return hi_; }
+    __device__ __forceinline__ double lo() const { return lo_; }
+    __device__ __forceinline__ double c5() const { return c5_; }
+    __device__ __forceinline__ double c4() const { return c4_; }
+    __device__ __forceinline__ double c3() const { return c3_; }
+    __device__ __forceinline__ double third() const { return third_; }
+    __device__ __forceinline__ double tab(int j) const
+    {
+        double v;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(tab_ + ((unsigned) j << 3)));
+        return v;
+    }
+};
+
+template <int KS>
+__device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const float *const *s_gv,
+                                                      const SegRec *seg, unsigned meta, int lane,
+                                                      const int (&koff)[KS], double (&Iv)[KS],
+                                                      const PinnedConsts &KC)
+{
+    const int lo = meta & 0xfff, hi = (meta >> 12) & 0xfff;
+    const int K = P.K;
+    for (int c0 = lo; c0 < hi; c0 += 32) {
+        const int cnt = min(32, hi - c0);
+        int4 rv = make_int4(0, 0, 0, 0);
+        if (lane < cnt)
+            rv = __ldg(reinterpret_cast<const int4 *>(&seg[c0 + lane]));
+        float gn[KS];
+        {
+            const float *row = s_gv[c0 / RTB_N_SUB + 1] + (size_t) __shfl_sync(0xffffffffu, rv.z, 0) * K;
+#pragma unroll
+            for (int q = 0; q < KS; q++)
+                gn[q] = __ldg(row + koff[q]);
+        }
+        for (int j = 0; j < cnt; j++) {
+            const float gvl = __int_as_float(__shfl_sync(0xffffffffu, rv.x, j));
+            const float evl = __int_as_float(__shfl_sync(0xffffffffu, rv.y, j));
+            float g[KS];
+#pragma unroll
+            for (int q = 0; q < KS; q++)
+                g[q] = gn[q];
+            if (j + 1 < cnt) {
+                const float *row = s_gv[(c0 + j + 1) / RTB_N_SUB + 1] +
+                                   (size_t) __shfl_sync(0xffffffffu, rv.z, j + 1) * K;
+#pragma unroll
+                for (int q = 0; q < KS; q++)
+                    gn[q] = __ldg(row + koff[q]);
+            }
+            if (gvl == 0.0f && evl == 0.0f)
+                continue; // gl = el = 0: the update is the identity
+            float glf[KS], elf[KS];
+            bool odd = false;
+#pragma unroll
+            for (int q = 0; q < KS; q++) {
+                glf[q] = __fmul_rn(gvl, g[q]);
+                elf[q] = __fmul_rn(evl, g[q]);
+                odd = odd || !(fabsf(glf[q]) < 700.0f);
+            }
+            if (__any_sync(0xffffffffu, odd)) { // |gl| >= 700, inf or NaN: library semantics
+#pragma unroll
+                for (int q = 0; q < KS; q++)
+                    Iv[q] = ase_update_library(Iv[q], (double) glf[q], (double) elf[q]);
+                continue;
+            }
+#pragma unroll
+            for (int q = 0; q < KS; q++) {
+                const bool small = fabsf(glf[q]) < 1e-3f; // == (fabs((double) glf) < 1e-3)
+                const unsigned b_small = __ballot_sync(0xffffffffu, small);
+                const double gl = (double) glf[q], el = (double) elf[q];
+                double a = 0.0, b = 0.0;
+                if (b_small != 0u) // warp-uniform: some lane takes the Taylor branch
+                    a = ase_update_small(Iv[q], gl, el, KC);
+                if (b_small != 0xffffffffu) // warp-uniform: some lane takes the exp branch
+                    b = ase_update_large(Iv[q], gl, el, rcp_approx(glf[q]), KC);
+                Iv[q] = small ? a : b;
+            }
+        }
     }
     bool neg = false, nan = false;
 #pragma unroll
@@ -493,14 +615,21 @@ __device__ __forceinline__ int integrate_ray(const DevProblem &P, const SegRec *
 }
 
 #define RTB_OWNER_WARPS 8
+#ifndef RTB_OWNER_MINBLOCKS
+#define RTB_OWNER_MINBLOCKS 3
+#endif
 
 template <int KS>
-__global__ void __launch_bounds__(RTB_OWNER_WARPS * 32)
+__global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, RTB_OWNER_MINBLOCKS)
     integrate_ase_owner_kernel(const DevProblem P, const Chunk c, const Handoff h, const Outputs o)
 {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double part[RTB_OWNER_WARPS][KS * 32];
     __shared__ double exp_tab[64];
-    load_exp_table(exp_tab);
+    const float **s_gv = reinterpret_cast<const float **>(smem_raw); // [N] gv base pointers
+    for (int i = threadIdx.x; i < P.N; i += blockDim.x)
+        s_gv[i] = P.planes[i].gv;
+    load_exp_table(exp_tab); // includes __syncthreads()
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long p = c.pix0 + blockIdx.x;
     const PixelRays pr = pixel_rays(P, p);
@@ -508,12 +637,15 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32)
     const int K = P.K;
     const long long slot0 = (long long) blockIdx.x * P.ab_max;
     double pix[KS], dv2[KS];
+    int koff[KS];
 #pragma unroll
     for (int q = 0; q < KS; q++) {
         pix[q] = 0.0;
         const int k = lane + 32 * q;
         dv2[q] = k < K ? __ldg(&P.dv2[k]) : 0.0;
+        koff[q] = min(k, K - 1); // lanes past the last bin recompute bin K-1 (never stored)
     }
+    const PinnedConsts KC(P.kfp_g, exp_tab);
     for (int t = warp; t < pr.cnt; t += RTB_OWNER_WARPS) {
         const long long slot = slot0 + t;
         const unsigned meta = __ldg(&h.meta[slot]);
@@ -523,7 +655,8 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32)
 #pragma unroll
         for (int q = 0; q < KS; q++)
             Iv[q] = 0.0;
-        const int code = integrate_ray<KS>(P, h.seg + slot * S, meta, lane, 0, Iv, exp_tab);
+        const int code =
+            integrate_ray_ase_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, koff, Iv, KC);
         const int ab = pr.ab0 + t * (int) P.n_parallel;
         const int ka = ab / P.snb, m = ab % P.snb;
         if (code != 0) {
@@ -567,11 +700,12 @@ void launch_integrate_ase_owner(const DevProblem &P, const Chunk &c, const Hando
     const unsigned blocks = (unsigned) npix;
     const int threads = RTB_OWNER_WARPS * 32;
     const int ks = (P.K + 31) / 32;
+    const size_t smem = sizeof(float *) * (size_t) P.N;
     switch (ks) {
-    case 1: integrate_ase_owner_kernel<1><<<blocks, threads, 0, st>>>(P, c, h, o); break;
-    case 2: integrate_ase_owner_kernel<2><<<blocks, threads, 0, st>>>(P, c, h, o); break;
-    case 3: integrate_ase_owner_kernel<3><<<blocks, threads, 0, st>>>(P, c, h, o); break;
-    default: integrate_ase_owner_kernel<4><<<blocks, threads, 0, st>>>(P, c, h, o); break;
+    case 1: integrate_ase_owner_kernel<1><<<blocks, threads, smem, st>>>(P, c, h, o); break;
+    case 2: integrate_ase_owner_kernel<2><<<blocks, threads, smem, st>>>(P, c, h, o); break;
+    case 3: integrate_ase_owner_kernel<3><<<blocks, threads, smem, st>>>(P, c, h, o); break;
+    default: integrate_ase_owner_kernel<4><<<blocks, threads, smem, st>>>(P, c, h, o); break;
     }
 }
 
@@ -625,6 +759,7 @@ __global__ void __launch_bounds__(RTB_FUSED_WARPS * 32, 2)
     for (int i = threadIdx.x; i < P.N; i += blockDim.x)
         s_gv[i] = P.planes[i].gv;
     load_exp_table(exp_tab); // includes __syncthreads()
+    const ArrayConsts KC{ P.kfp, exp_tab };
 
     const long long p = pix0 + blockIdx.x;
     const PixelRays pr = pixel_rays(P, p);
@@ -723,9 +858,9 @@ __global__ void __launch_bounds__(RTB_FUSED_WARPS * 32, 2)
                     } else {
                         double a = 0.0, bb = 0.0;
                         if (b_small != 0u)
-                            a = ase_update_small(Iv[q], gl, el);
+                            a = ase_update_small(Iv[q], gl, el, KC);
                         if (b_small != 0xffffffffu)
-                            bb = ase_update_large(Iv[q], gl, el, rcp_approx(glf), exp_tab);
+                            bb = ase_update_large(Iv[q], gl, el, rcp_approx(glf), KC);
                         Iv[q] = small ? a : bb;
                     }
                 }

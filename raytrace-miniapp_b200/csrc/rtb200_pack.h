@@ -128,6 +128,12 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
     out.dz0 = (float) e.dz;
     out.c = 0.5f;
     out.use_emis = (p.gain[0].E0 != nullptr && p.seed == nullptr) ? 1 : 0; // :402
+    const double kfp[RTB_K_COUNT] = { RTB_K_VALUES };
+    std::memcpy(out.kfp, kfp, sizeof(kfp));
+
+    double *kfp_g = blob.alloc<double>(RTB_K_COUNT, &out.kfp_g);
+    if (fill)
+        std::memcpy(kfp_g, kfp, sizeof(kfp));
 
     // ---- gain planes ------------------------------------------------------------------------
     DevPlane *planes = blob.alloc<DevPlane>((size_t) N, &out.planes);

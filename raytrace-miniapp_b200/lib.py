@@ -37,7 +37,9 @@ class RaysFailed(RuntimeError):
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "librtb200.so")
+    """In-tree librtb200.so; RTB200_LIB selects another build of the same library (A/B tuning)."""
+    return os.environ.get("RTB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                        "librtb200.so")
 
 
 def load():

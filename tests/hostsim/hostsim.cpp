@@ -127,10 +127,12 @@ int hostsim_find_cell(const double *X, int n, double Y)
 
 // FP64 update doors (rtb200_fp64.cuh): the fast exp and the two update branches.
 static const double k_exp_table[64] = { RTB_EXP_TABLE_VALUES };
+static const double k_fp[RTB_K_COUNT] = { RTB_K_VALUES };
+static const ArrayConsts k_consts = { k_fp, k_exp_table };
 void hostsim_exp(const double *x, double *y, int n)
 {
     for (int i = 0; i < n; i++)
-        y[i] = exp_any(x[i], k_exp_table);
+        y[i] = exp_any(x[i], k_consts);
 }
 // One update with float inputs gvl, evl, g as the kernel forms them; branch chosen like the kernel.
 double hostsim_ase_update(double Iv, float gvl, float evl, float g)
@@ -140,8 +142,8 @@ double hostsim_ase_update(double Iv, float gvl, float evl, float g)
     if (!(fabsf(glf) < 700.0f))
         return -1.0; // library path on the device
     if (fabsf(glf) < 1e-3f)
-        return ase_update_small(Iv, gl, el);
-    return ase_update_large(Iv, gl, el, 1.0f / glf, k_exp_table);
+        return ase_update_small(Iv, gl, el, k_consts);
+    return ase_update_large(Iv, gl, el, 1.0f / glf, k_consts);
 }
 
 } // extern "C"
