@@ -58,6 +58,10 @@ struct DevProblem {
     //     coordinate is outside the seed grid (calc_seed_inline's range test, :235-237)
     const double *seed_fx, *seed_fy, *seed_fa, *seed_fb, *seed_fv;
     double seed_f0;
+    // the raw seed tables (ray_seed_struct x[d], f[d], d = x, y, a, b) for explicit ray lists,
+    // where the seed is interpolated per ray on the device
+    const double *sd_x[4], *sd_f[4];
+    int sd_dim[4];
     // --- constants of the FP64 update (rtb200_fp64.cuh), kept in the kernel parameter bank
     double kfp[RTB_K_COUNT];
     const double *kfp_g; // the same constants in the staged blob (read once with volatile loads)

@@ -669,11 +669,6 @@ int rtb200_trace_rays(rtb200_ctx *ctx, int N, const rtb200_beam *beam,
             ctx->err = "rtb200_trace_rays: bad argument";
         return RTB200_ERR_ARG;
     }
-    if (seed) {
-        ctx->err = "rtb200_trace_rays: explicit ray lists with a seed beam are not supported yet "
-                   "(use rtb200_create_image)";
-        return RTB200_ERR_ARG;
-    }
     rtb200_problem p;
     std::memset(&p, 0, sizeof(p));
     p.N = N;
@@ -682,7 +677,9 @@ int rtb200_trace_rays(rtb200_ctx *ctx, int N, const rtb200_beam *beam,
     p.euv_beam = beam;
     p.gain = gain;
     p.seed = seed;
+    p.seed_beam = seed ? beam : nullptr; // only consulted by the validation (grids are the euv ones)
     int rc = validate(ctx, &p, RTB200_FLAG_NO_LIMITS);
+    p.seed_beam = nullptr;
     if (rc)
         return rc;
     reset_timing(ctx);
@@ -734,10 +731,6 @@ int rtb200_calc_rays(rtb200_ctx *ctx, int N, double dz, const rtb200_gain_plane 
             ctx->err = "rtb200_calc_rays: bad argument";
         return RTB200_ERR_ARG;
     }
-    if (seed) {
-        ctx->err = "rtb200_calc_rays: seed beams are not supported yet";
-        return RTB200_ERR_ARG;
-    }
     rtb200_beam beam;
     std::memset(&beam, 0, sizeof(beam));
     beam.nv = K;
@@ -748,6 +741,7 @@ int rtb200_calc_rays(rtb200_ctx *ctx, int N, double dz, const rtb200_gain_plane 
     p.N_parallel = 1;
     p.euv_beam = &beam;
     p.gain = gain;
+    p.seed = seed;
     if (N < 1 || (N - 1) * RTB200_N_SUB > RTB_MAX_SEGS) {
         ctx->err = "rtb200_calc_rays: bad N";
         return RTB200_ERR_ARG;

@@ -972,6 +972,80 @@ __device__ __forceinline__ int dev_get_index(int n, const double *x, double dx, 
     return hi;
 }
 
+// findfirstsingle / interp_pchip / calc_seed_inline (RayTraceImageHelper.h:101-117, :168-247)
+// on the device, for explicit ray lists with a seed beam.  The seed amplitude multiplies the
+// spectrum (it feeds no discrete decision), so ordinary FP64 arithmetic is sufficient.
+__device__ int dev_findfirstsingle(const double *X, int n, double Y)
+{
+    if (Y < __ldg(&X[0]))
+        return 0;
+    if (Y > __ldg(&X[n - 1]))
+        return n;
+    int lo = 0, hi = n - 1;
+    while (hi - lo != 1) {
+        const int mid = (hi + lo) / 2;
+        if (__ldg(&X[mid]) >= Y)
+            hi = mid;
+        else
+            lo = mid;
+    }
+    return hi;
+}
+
+__device__ double dev_interp_pchip(int N, const double *xi, const double *yi, double x)
+{
+    if (x <= xi[0] || N <= 2) {
+        const double t = (x - xi[0]) / (xi[1] - xi[0]);
+        return (1.0 - t) * yi[0] + t * yi[1];
+    }
+    if (x >= xi[N - 1]) {
+        const double t = (x - xi[N - 2]) / (xi[N - 1] - xi[N - 2]);
+        return (1.0 - t) * yi[N - 2] + t * yi[N - 1];
+    }
+    const int i = dev_findfirstsingle(xi, N, x);
+    const double f1 = yi[i - 1], f2 = yi[i];
+    const double t = (x - xi[i - 1]) / (xi[i] - xi[i - 1]);
+    double g1 = 0, g2 = 0;
+    if (i <= 1) {
+        g1 = f2 - f1;
+    } else if ((f1 < f2 && f1 > yi[i - 2]) || (f1 > f2 && f1 < yi[i - 2])) {
+        const double f0 = yi[i - 2];
+        const double h1 = xi[i - 1] - xi[i - 2], h2 = xi[i] - xi[i - 1];
+        const double a1 = (h2 - h1) / h1, a2 = h1 / (h1 + h2);
+        g1 = a1 * (f1 - f0) + a2 * (f2 - f0);
+        const double s1 = fabs(f1 - f0) / h1, s2 = fabs(f2 - f1) / h2;
+        const double g_max = 2 * h2 * (s1 < s2 ? s1 : s2);
+        g1 = ((g1 >= 0) ? 1 : -1) * (fabs(g1) < g_max ? fabs(g1) : g_max);
+    }
+    if (i >= N - 1) {
+        g2 = f2 - f1;
+    } else if ((f2 < f1 && f2 > yi[i + 1]) || (f2 > f1 && f2 < yi[i + 1])) {
+        const double f0 = yi[i + 1];
+        const double h1 = xi[i] - xi[i - 1], h2 = xi[i + 1] - xi[i];
+        const double a1 = -h2 / (h1 + h2), a2 = (h2 - h1) / h2;
+        g2 = a1 * (f1 - f0) + a2 * (f2 - f0);
+        const double s1 = fabs(f2 - f1) / h1, s2 = fabs(f0 - f2) / h2;
+        const double g_max = 2 * h1 * (s1 < s2 ? s1 : s2);
+        g2 = ((g2 >= 0) ? 1 : -1) * (fabs(g2) < g_max ? fabs(g2) : g_max);
+    }
+    const double t2 = t * t;
+    return f1 + t2 * (2 * t - 3) * (f1 - f2) + t * g1 - t2 * (g1 + (1 - t) * (g1 + g2));
+}
+
+__device__ double dev_calc_seed(const DevProblem &P, double x, double y, double a, double b)
+{
+    const double v[4] = { x, y, a, b };
+    double f = P.seed_f0;
+    for (int d = 0; d < 4; d++) {
+        const int n = P.sd_dim[d];
+        if (!(v[d] >= P.sd_x[d][0] && v[d] <= P.sd_x[d][n - 1]))
+            return 0.0;
+    }
+    for (int d = 0; d < 4; d++)
+        f *= dev_interp_pchip(P.sd_dim[d], P.sd_x[d], P.sd_f[d], v[d]);
+    return f < 0.0 ? 0.0 : f;
+}
+
 // One warp per ray slot; K is covered in passes of 64 bins.  Handles both integration modes,
 // both ray sources, scatter binning and the per-ray dumps.
 template <bool LIST>
@@ -996,6 +1070,14 @@ __global__ void __launch_bounds__(256)
         if (LIST) {
             const float4 r = __ldg(&c.rays[c.ray0 + slot]);
             rx = r.x, ry = r.y, ra = r.z, rb = r.w;
+            if (P.seed_fv && !(meta & (RTB_META_ESCAPED | RTB_META_INVALID))) {
+                if (P.method == 1) { // backward: seed at the exit point (:525-529)
+                    const float4 e = h.exit_ray[slot];
+                    f = dev_calc_seed(P, (double) e.x, (double) e.y, (double) e.z, (double) e.w);
+                } else { // forward: seed at the entry point (:530-533)
+                    f = dev_calc_seed(P, (double) rx, (double) ry, (double) ra, (double) rb);
+                }
+            }
         } else {
             const long long p = c.pix0 + slot / P.ab_max;
             const int t = (int) (slot % P.ab_max);

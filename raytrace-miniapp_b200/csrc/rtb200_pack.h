@@ -206,6 +206,15 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
         if (fill)
             std::memcpy(fv, p.seed->f[4], sizeof(double) * p.seed->dim[4]);
         out.seed_f0 = p.seed->f0;
+        for (int d = 0; d < 4; d++) {
+            out.sd_dim[d] = p.seed->dim[d];
+            double *x = blob.alloc<double>((size_t) p.seed->dim[d], &out.sd_x[d]);
+            double *f = blob.alloc<double>((size_t) p.seed->dim[d], &out.sd_f[d]);
+            if (fill) {
+                std::memcpy(x, p.seed->x[d], sizeof(double) * p.seed->dim[d]);
+                std::memcpy(f, p.seed->f[d], sizeof(double) * p.seed->dim[d]);
+            }
+        }
     }
     if (explicit_rays) {
         out.method = method_in;

@@ -1,0 +1,145 @@
+// RayTraceImageB200.cpp — the reference-side back-end loop of the B200 path.
+//
+// This is the file a maintainer of the reference adds next to src/RayTraceImageCPU.cpp and
+// src/RayTraceImageCuda.cu: it has the exact `RayTraceImage<Backend>Loop` signature that
+// RayTrace::create_image dispatches to (extern declarations at src/RayTraceImage.cpp:47-75,
+// call sites :350-423) and forwards to the C ABI of include/rtb200.h (librtb200.so).  It is
+// compiled against the reference's own headers, so it is built only where the reference
+// checkout exists (oracle/Makefile, target `b200`); nothing in librtb200.so depends on it.
+//
+// Behaviour mirrored from the reference's loops:
+//  * image / I_ang are accumulated into (src/RayTraceImageCPU.cpp:56-68);
+//  * failed rays are appended to failed_rays and their codes OR-ed into failure_code
+//    (:32-36); the caller then aborts with "Some rays failed";
+//  * device / runtime errors print a message and exit(-1), like CUDA_CHECK
+//    (src/RayTraceImageCuda.cu:8-18);
+//  * re-entrant: one rtb200 context per host thread (the legacy CUDA loop keeps
+//    non-thread-safe static state, src/RayTraceImageCuda.cu:153-160).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <vector>
+
+#include "RayTrace.h"
+#include "common/RayTraceImageHelper.h"
+
+#include "rtb200.h"
+
+namespace {
+
+struct ThreadContext {
+    rtb200_ctx *ctx = nullptr;
+    int device = -1;
+    ~ThreadContext() { rtb200_destroy(ctx); }
+};
+thread_local ThreadContext tls;
+std::mutex pending_mutex;
+std::deque<int> pending_devices; // devices announced by the parent for workers not yet started
+
+rtb200_ctx *context()
+{
+    int device = -1;
+    if (!tls.ctx) { // a fresh worker thread takes the next announced device, if any
+        std::lock_guard<std::mutex> lock(pending_mutex);
+        if (!pending_devices.empty()) {
+            device = pending_devices.front();
+            pending_devices.pop_front();
+        }
+    } else {
+        device = tls.device;
+    }
+    if (device < 0) {
+        const char *e = getenv("RTB200_DEVICE");
+        device = e ? atoi(e) : 0;
+    }
+    if (tls.ctx && tls.device == device)
+        return tls.ctx;
+    rtb200_destroy(tls.ctx);
+    tls.ctx = nullptr;
+    if (rtb200_create(device, &tls.ctx) != RTB200_OK) {
+        fprintf(stderr, "rtb200: no usable CUDA device %d (the b200 method has no CPU fallback)\n", device);
+        exit(-1);
+    }
+    tls.device = device;
+    return tls.ctx;
+}
+
+} // namespace
+
+// setID hook for RayTraceImageThreadLoop ("b200-multigpu").  The reference calls setID(i) in the
+// PARENT thread just before it starts worker i (src/RayTraceImage.cpp:116-119), so its setGPU
+// (cudaSetDevice, :82-88) never reaches the worker and every worker lands on device 0.  Here the
+// parent only announces the device; each freshly started worker thread picks one announcement up
+// when it creates its context, so the N workers run on N distinct devices.
+void RayTraceImageB200SetDevice(int device)
+{
+    std::lock_guard<std::mutex> lock(pending_mutex);
+    pending_devices.push_back(device);
+}
+
+void RayTraceImageB200Loop(int N, const RayTrace::EUV_beam_struct &beam,
+    const RayTrace::ray_gain_struct *gain, const RayTrace::ray_seed_struct *seed, int method,
+    const std::vector<ray_struct> &rays, double scale, double *image, double *I_ang,
+    unsigned int &failure_code, std::vector<ray_struct> &failed_rays)
+{
+    static_assert(sizeof(ray_struct) == sizeof(rtb200_ray), "ray_struct layout");
+    failure_code = 0;
+    rtb200_beam b;
+    memset(&b, 0, sizeof(b));
+    b.nx = beam.nx;
+    b.ny = beam.ny;
+    b.na = beam.na;
+    b.nb = beam.nb;
+    b.nv = beam.nv;
+    b.dx = beam.dx;
+    b.dy = beam.dy;
+    b.da = beam.da;
+    b.db = beam.db;
+    b.dz = beam.dz;
+    b.x = beam.x;
+    b.y = beam.y;
+    b.a = beam.a;
+    b.b = beam.b;
+    b.dv = beam.dv;
+    std::vector<rtb200_gain_plane> planes(N);
+    for (int i = 0; i < N; i++) {
+        planes[i].Nx = gain[i].Nx;
+        planes[i].Ny = gain[i].Ny;
+        planes[i].Nv = gain[i].Nv;
+        planes[i].x = gain[i].x;
+        planes[i].y = gain[i].y;
+        planes[i].n = gain[i].n;
+        planes[i].g0 = gain[i].g0;
+        planes[i].E0 = gain[i].E0;
+        planes[i].gv = gain[i].gv;
+    }
+    rtb200_seed sd;
+    if (seed) {
+        for (int i = 0; i < 5; i++) {
+            sd.dim[i] = seed->dim[i];
+            sd.x[i] = seed->x[i];
+            sd.f[i] = seed->f[i];
+        }
+        sd.f0 = seed->f0;
+    }
+    rtb200_ctx *ctx = context();
+    rtb200_ray failed[RTB200_N_FAILED_MAX];
+    int n_failed = 0;
+    const int rc = rtb200_trace_rays(ctx, N, &b, planes.data(), seed ? &sd : nullptr, method,
+        reinterpret_cast<const rtb200_ray *>(rays.data()), rays.size(), scale, image, I_ang,
+        &failure_code, failed, RTB200_N_FAILED_MAX, &n_failed);
+    if (rc < 0) {
+        fprintf(stderr, "rtb200 error %d: %s\n", rc, rtb200_last_error(ctx));
+        exit(-1);
+    }
+    for (int i = 0; i < n_failed && i < RTB200_N_FAILED_MAX; i++) {
+        ray_struct r;
+        r.x = failed[i].x;
+        r.y = failed[i].y;
+        r.a = failed[i].a;
+        r.b = failed[i].b;
+        failed_rays.push_back(r);
+    }
+}
