@@ -162,6 +162,14 @@ int64_t rtb200_staged_rays(const rtb200_ctx *ctx);
  * rtb200_sync.  `cuda_stream` = 0 uses the context's own stream, else a cudaStream_t. */
 int rtb200_launch(rtb200_ctx *ctx, int64_t pix_begin, int64_t pix_end, double *d_image,
                   double *d_I_ang, void *cuda_stream);
+/* Same, for the image rows j = row_offset, row_offset + row_stride, ... (source-grid rows).
+ * This is the multi-GPU decomposition: rank r of W traces rows r, r + W, ... so that the
+ * ranks' work is balanced; results land at their true positions in the full-size buffers,
+ * and the exchange is a sum (the rows of different ranks are disjoint).  It plays the role of
+ * the reference's strided N_start / N_parallel decomposition (src/RayTraceImage.cpp:300-308)
+ * at pixel-row granularity, which keeps every pixel's spectrum on one device. */
+int rtb200_launch_rows(rtb200_ctx *ctx, int row_offset, int row_stride, double *d_image,
+                       double *d_I_ang, void *cuda_stream);
 int rtb200_sync(rtb200_ctx *ctx, unsigned *failure_code, rtb200_ray *failed, int max_failed,
                 int *n_failed);
 int rtb200_get_timings(const rtb200_ctx *ctx, rtb200_timings *out);

@@ -293,12 +293,12 @@ int ensure_handoff(rtb200_ctx *ctx, long long slots, bool need_exit)
 
 // Launches the kernels for source pixels [pix0, pix1) in chunks whose hand-off fits the budget.
 int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs &out,
-                  cudaStream_t st)
+                  cudaStream_t st, int row_off = 0, int row_stride = 1)
 {
     const DevProblem &P = ctx->prob;
     if (pix1 <= pix0)
         return RTB200_OK;
-    if (ctx->owner_ok && !out.Iv && !out.error && ctx->use_fused) {
+    if (ctx->owner_ok && !out.Iv && !out.error && ctx->use_fused && row_stride == 1) {
         const size_t e0 = new_event(ctx, st);
         if (launch_trace_ase_fused(P, pix0, pix1, out, st)) {
             const size_t e1 = new_event(ctx, st);
@@ -324,6 +324,8 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
         std::memset(&c, 0, sizeof(c));
         c.pix0 = a;
         c.pix1 = std::min(pix1, a + pix_per_chunk);
+        c.row_off = row_off;
+        c.row_stride = row_stride;
         const size_t e0 = new_event(ctx, st);
         launch_march(P, c, false, h, ctx->d_fail, ctx->count_steps, st, ctx->d_work, ctx->flat_march);
         const size_t e1 = new_event(ctx, st);
@@ -500,6 +502,32 @@ int rtb200_launch(rtb200_ctx *ctx, int64_t pix_begin, int64_t pix_end, double *d
         reset_timing(ctx);
     Outputs out{ d_image, d_I_ang, nullptr, nullptr, ctx->d_fail };
     return launch_pixels(ctx, pix_begin, pix_end, out, st);
+}
+
+int rtb200_launch_rows(rtb200_ctx *ctx, int row_offset, int row_stride, double *d_image,
+                       double *d_I_ang, void *cuda_stream)
+{
+    if (!ctx || !ctx->staged || !d_image || !d_I_ang || row_stride < 1 || row_offset < 0 ||
+        row_offset >= row_stride) {
+        if (ctx)
+            ctx->err = "rtb200_launch_rows: nothing staged or bad argument";
+        return RTB200_ERR_ARG;
+    }
+    RTB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : ctx->stream;
+    if (st != ctx->stream) { // order after the staging upload
+        cudaEvent_t e;
+        RTB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        RTB_CUDA(cudaEventRecord(e, ctx->stream));
+        RTB_CUDA(cudaStreamWaitEvent(st, e, 0));
+        RTB_CUDA(cudaEventDestroy(e));
+    }
+    if (ctx->ev_used > 64 + 3 * 4096)
+        reset_timing(ctx);
+    const DevProblem &P = ctx->prob;
+    const long long rows = P.sny > row_offset ? (P.sny - row_offset + row_stride - 1) / row_stride : 0;
+    Outputs out{ d_image, d_I_ang, nullptr, nullptr, ctx->d_fail };
+    return launch_pixels(ctx, 0, rows * P.snx, out, st, row_offset, row_stride);
 }
 
 int rtb200_sync(rtb200_ctx *ctx, unsigned *failure_code, rtb200_ray *failed, int max_failed,

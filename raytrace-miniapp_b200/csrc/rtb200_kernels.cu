@@ -55,6 +55,17 @@ __device__ __forceinline__ PixelRays pixel_rays(const DevProblem &P, long long p
     return r;
 }
 
+// Logical -> physical source pixel.  Contiguous tiles use row_stride = 1 (identity); the
+// multi-GPU sharding gives rank r the image rows r, r + world, r + 2*world, ... so that the
+// ranks' work is balanced (rows near the target surface escape early, rows far from it do not).
+__device__ __forceinline__ long long phys_pixel(const DevProblem &P, const Chunk &c, long long q)
+{
+    if (c.row_stride == 1)
+        return q;
+    const long long jr = q / P.snx;
+    return ((long long) c.row_off + jr * c.row_stride) * P.snx + (q - jr * P.snx);
+}
+
 __device__ __forceinline__ void report_failure(FailState *fail, int code, float x, float y,
                                                float a, float b)
 {
@@ -166,7 +177,7 @@ __global__ void __launch_bounds__(128) march_kernel(const DevProblem P, const Ch
         const long long npix = c.pix1 - c.pix0;
         if (L >= npix * P.ab_max)
             return;
-        const long long p = c.pix0 + L / P.ab_max;
+        const long long p = phys_pixel(P, c, c.pix0 + L / P.ab_max);
         const int t = (int) (L % P.ab_max);
         const PixelRays pr = pixel_rays(P, p);
         if (t >= pr.cnt) {
@@ -254,7 +265,7 @@ __global__ void __launch_bounds__(128) march_flat_kernel(const DevProblem P, con
                         const float2 t = __ldg(&c.tans[c.ray0 + L]);
                         rx = r.x, ry = r.y, ra = r.z, rb = r.w, ta = t.x, tb = t.y;
                     } else {
-                        const long long p = c.pix0 + L / P.ab_max;
+                        const long long p = phys_pixel(P, c, c.pix0 + L / P.ab_max);
                         const int t = (int) (L % P.ab_max);
                         const PixelRays pr = pixel_rays(P, p);
                         active = t < pr.cnt;
@@ -631,7 +642,7 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, RTB_OWNER_MINBLOCKS)
         s_gv[i] = P.planes[i].gv;
     load_exp_table(exp_tab); // includes __syncthreads()
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long p = c.pix0 + blockIdx.x;
+    const long long p = phys_pixel(P, c, c.pix0 + blockIdx.x);
     const PixelRays pr = pixel_rays(P, p);
     const int S = (P.N - 1) * RTB_N_SUB;
     const int K = P.K;
@@ -1079,7 +1090,7 @@ __global__ void __launch_bounds__(256)
                 }
             }
         } else {
-            const long long p = c.pix0 + slot / P.ab_max;
+            const long long p = phys_pixel(P, c, c.pix0 + slot / P.ab_max);
             const int t = (int) (slot % P.ab_max);
             const PixelRays pr = pixel_rays(P, p);
             const int ab = pr.ab0 + t * (int) P.n_parallel;

@@ -10,7 +10,8 @@ namespace rtb {
 // A contiguous range of source pixels [pix0, pix1) in x-fastest order (p = i + j*snx), or, in
 // list mode, a contiguous range of explicit rays.
 struct Chunk {
-    long long pix0, pix1;   // grid mode
+    long long pix0, pix1;   // grid mode: LOGICAL pixel range; physical pixel = phys_pixel(q)
+    int row_off, row_stride; // row-cyclic sharding: physical row = row_off + (q / snx)*row_stride
     long long ray0, ray1;   // list mode (explicit rays)
     const float4 *rays;     // list mode: (x, y, a, b) per ray
     const float2 *tans;     // list mode: host tanf(1e-3f*a), tanf(1e-3f*b) per ray

@@ -5,8 +5,9 @@ sharded axis): rank r traces the contiguous pixel range tile_bounds(n, world, r)
 image rows exclusively (ASE).  The exchange step that follows the kernels is the one the full
 application performs over MPI (intensity_step_struct::sum_reduce,
 src/RayTraceStructures.cpp:1603-1646), restated for device-resident partials:
-  ASE    : all_gather of the equal-sized image tiles + all_reduce(sum) of I_ang
-  seeded : all_reduce(sum) of the full image and of I_ang (scatter binning)
+  contiguous tiles, ASE : all_gather of the equal-sized image tiles + all_reduce(sum) of I_ang
+  row-cyclic (default)  : all_reduce(sum) of the full image (rows are disjoint) and of I_ang
+  seeded                : all_reduce(sum) of the full image and of I_ang (scatter binning)
 over NCCL / NVLink on GPUs, gloo in the CPU tests.
 """
 import torch
@@ -43,14 +44,29 @@ def exchange(image, I_ang, n_pixels, nv, method, group=None):
     return image, I_ang
 
 
-def sharded_create_image(ctx, problem, image, I_ang, group=None, stream=None):
+def exchange_rows(image, I_ang, group=None):
+    """Exchange for the row-cyclic decomposition: every rank holds a full-size image with only
+    its own rows filled (the others zero), so the gather is a sum; x + 0 is exact, hence the
+    result is bit-identical to the single-device image in ASE mode."""
+    if dist.get_world_size(group) > 1:
+        dist.all_reduce(image, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(I_ang, op=dist.ReduceOp.SUM, group=group)
+    return image, I_ang
+
+
+def sharded_create_image(ctx, problem, image, I_ang, group=None, stream=None, cyclic=True):
     """Stage-free step: `ctx` already holds the staged problem.  Zeroes the buffers, traces this
-    rank's tile on `stream` (default: torch's current stream) and exchanges.  Asynchronous."""
+    rank's share on `stream` (default: torch's current stream) and exchanges.  Asynchronous.
+    cyclic=True: image rows rank, rank + world, ... (balanced; exchange = all_reduce);
+    cyclic=False: one contiguous tile per rank (exchange = all_gather of the tiles)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    n = ctx.staged_pixels
-    lo, hi, _ = tile_bounds(n, world, rank)
     image.zero_()
     I_ang.zero_()
     st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+    if cyclic:
+        ctx.launch_rows(rank, world, image, I_ang, stream=st)
+        return exchange_rows(image, I_ang, group)
+    n = ctx.staged_pixels
+    lo, hi, _ = tile_bounds(n, world, rank)
     ctx.launch(lo, hi, image, I_ang, stream=st)
     return exchange(image, I_ang, n, problem.euv_beam.nv, problem.method, group)

@@ -75,6 +75,7 @@ def load():
     L.rtb200_staged_rays.argtypes = [ctx]
     L.rtb200_staged_rays.restype = C.c_int64
     L.rtb200_launch.argtypes = [ctx, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.rtb200_launch_rows.argtypes = [ctx, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.rtb200_sync.argtypes = [ctx, P(C.c_uint), P(abi.Ray), C.c_int, P(C.c_int)]
     L.rtb200_get_timings.argtypes = [ctx, P(abi.Timings)]
     L.rtb200_reset_timings.argtypes = [ctx]
@@ -213,6 +214,13 @@ class Context:
             stream = 1  # cudaStreamLegacy
         self._check(self.L.rtb200_launch(self.h, pix_begin, pix_end, _addr(d_image),
                                          _addr(d_I_ang), stream))
+
+    def launch_rows(self, row_offset, row_stride, d_image, d_I_ang, stream=None):
+        """Trace the image rows row_offset, row_offset + row_stride, ... (multi-GPU sharding)."""
+        if stream is not None and stream == 0:
+            stream = 1  # cudaStreamLegacy
+        self._check(self.L.rtb200_launch_rows(self.h, row_offset, row_stride, _addr(d_image),
+                                              _addr(d_I_ang), stream))
 
     def sync(self, raise_on_failed=True):
         fc, nf = C.c_uint(0), C.c_int(0)

@@ -53,6 +53,14 @@ def _worker(rank, world, port, nx_keep, out):
         if rank == 0:
             np.save(out + "_image.npy", image.numpy())
             np.save(out + "_iang.npy", I_ang.numpy())
+        # row-cyclic decomposition: rows rank, rank + world, ...; exchange = sum of disjoint rows
+        rows_sel = [j for j in range(e.ny) if j % world == rank]
+        sel2 = np.concatenate([rays[i, j] for j in rows_sel for i in range(e.nx)])
+        r2 = pyoracle.Oracle().trace_rays(p, sel2, 1, 1.0)
+        img2, ang2 = torch.from_numpy(r2["image"].copy()), torch.from_numpy(r2["I_ang"].copy())
+        rdist.exchange_rows(img2, ang2)
+        if rank == 0:
+            np.save(out + "_image_cyclic.npy", img2.numpy())
         # seeded-style exchange: plain sums of full-size partials
         a = torch.full((12,), float(rank + 1), dtype=torch.float64)
         b = torch.full((5,), 10.0 * (rank + 1), dtype=torch.float64)
@@ -71,6 +79,7 @@ def test_two_rank_tiles_equal_single_process(nx_keep, oracle, tmp_path):
     full = oracle.create_image(p)
     img, ang = np.load(out + "_image.npy"), np.load(out + "_iang.npy")
     assert np.array_equal(img, full["image"])
+    assert np.array_equal(np.load(out + "_image_cyclic.npy"), full["image"])
     assert rel_l2(ang, full["I_ang"]) < 1e-14
     assert np.linalg.norm(img) > 0
 

@@ -177,3 +177,29 @@ def test_device_tiles_equal_whole_image(ase_small, ctx):
     ctx.sync()
     assert torch.equal(tile_i, whole_i)
     assert rel_l2(tile_a.cpu().numpy(), whole_a.cpu().numpy()) < 1e-14
+
+
+def test_row_cyclic_shares_equal_whole_image(ase_small, ctx):
+    """The multi-GPU decomposition (rows r, r + W, ...) emulated on one device: the W shares sum
+    to the single-launch image bit for bit."""
+    import torch
+    p, _ = ase_small
+    e = p.euv_beam
+    n = ctx.stage(p)
+    whole_i = torch.zeros(e.nx * e.ny * e.nv, dtype=torch.float64, device="cuda")
+    whole_a = torch.zeros(e.na * e.nb, dtype=torch.float64, device="cuda")
+    ctx.launch(0, n, whole_i, whole_a)
+    ctx.sync()
+    for world in (2, 3, 8):
+        acc_i, acc_a = torch.zeros_like(whole_i), torch.zeros_like(whole_a)
+        for r in range(world):
+            part_i, part_a = torch.zeros_like(whole_i), torch.zeros_like(whole_a)
+            ctx.launch_rows(r, world, part_i, part_a)
+            ctx.sync()
+            rows = part_i.view(e.ny, e.nx * e.nv)
+            other = [j for j in range(e.ny) if j % world != r]
+            assert not rows[other].any()  # a rank never touches another rank's rows
+            acc_i += part_i
+            acc_a += part_a
+        assert torch.equal(acc_i, whole_i)
+        assert rel_l2(acc_a.cpu().numpy(), whole_a.cpu().numpy()) < 1e-14

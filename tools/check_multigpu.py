@@ -34,13 +34,16 @@ def main():
         ctx.stage(p)
         image = torch.zeros(e.nx * e.ny * e.nv, dtype=torch.float64, device=dev)
         I_ang = torch.zeros(e.na * e.nb, dtype=torch.float64, device=dev)
-        rdist.sharded_create_image(ctx, p, image, I_ang)
+        rdist.sharded_create_image(ctx, p, image, I_ang)  # row-cyclic shares + all_reduce
+        ctx.sync()
+        tile_i, tile_a = torch.zeros_like(image), torch.zeros_like(I_ang)
+        rdist.sharded_create_image(ctx, p, tile_i, tile_a, cyclic=False)  # contiguous tiles + all_gather
         ctx.sync()
         whole_i, whole_a = torch.zeros_like(image), torch.zeros_like(I_ang)
         ctx.launch(0, ctx.staged_pixels, whole_i, whole_a, stream=torch.cuda.current_stream().cuda_stream)
         ctx.sync()
         if p.method == 1:
-            same = torch.equal(image, whole_i)
+            same = torch.equal(image, whole_i) and torch.equal(tile_i, whole_i)
         else:
             same = float((image - whole_i).norm() / whole_i.norm()) < 1e-12
         ea = float((I_ang - whole_a).norm() / whole_a.norm())
