@@ -146,7 +146,24 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
         double *y = blob.alloc<double>((size_t) g.Ny, &P.y);
         Node *node = blob.alloc<Node>(nn, &P.node);
         float *gv = blob.alloc<float>(nn * (size_t) K, &P.gv);
+        double *rwx = blob.alloc<double>((size_t) g.Nx, &P.rwx);
+        double *rdx = blob.alloc<double>((size_t) g.Nx, &P.rdx);
+        double *rwy = blob.alloc<double>((size_t) g.Ny, &P.rwy);
+        double *rdy = blob.alloc<double>((size_t) g.Ny, &P.rdy);
         if (fill) {
+            bool ok = true;
+            auto recip = [&ok](const double *c, int n, double *rw, double *rd) {
+                rw[0] = rd[0] = 0.0;
+                for (int k = 1; k < n; k++) {
+                    const double w = c[k] - c[k - 1];
+                    rw[k] = 1.0 / w;
+                    rd[k] = 1.0 / (double) (float) w;
+                    ok = ok && std::isnormal(rw[k]) && std::isnormal(rd[k]) && std::isnormal(w);
+                }
+            };
+            recip(g.x, g.Nx, rwx, rdx);
+            recip(g.y, g.Ny, rwy, rdy);
+            P.fast_div = ok ? 1 : 0;
             std::memcpy(x, g.x, sizeof(double) * g.Nx);
             std::memcpy(y, g.y, sizeof(double) * g.Ny);
             for (size_t q = 0; q < nn; q++) {

@@ -146,4 +146,67 @@ double hostsim_ase_update(double Iv, float gvl, float evl, float g)
     return ase_update_large(Iv, gl, el, 1.0f / glf, k_consts);
 }
 
+// Exactness doors for the division shortcuts of rtb200_math.cuh.
+// Random operand pairs for ddiv_by; returns the number of mismatches against `/`.
+long long hostsim_check_ddiv_by(long long n, unsigned long long seed)
+{
+    unsigned long long st = seed * 2862933555777941757ULL + 3037000493ULL;
+    auto next = [&]() {
+        st ^= st << 13;
+        st ^= st >> 7;
+        st ^= st << 17;
+        return st;
+    };
+    long long bad = 0;
+    for (long long i = 0; i < n; i++) {
+        // a: signed, magnitude 2^[-40, 10); b: positive, magnitude 2^[-30, 0); random mantissas
+        const unsigned long long ma = next(), mb = next();
+        const int ea = (int) (next() % 50) - 40, eb = (int) (next() % 30) - 30;
+        double a = ldexp(1.0 + (double) (ma >> 12) / 4503599627370496.0, ea);
+        if (ma & 1)
+            a = -a;
+        const double b = ldexp(1.0 + (double) (mb >> 12) / 4503599627370496.0, eb);
+        const double rb = 1.0 / b;
+        if (ddiv_by(a, b, rb) != a / b)
+            bad++;
+    }
+    return bad;
+}
+// Every float in [lo_bits, hi_bits] (bit patterns, both signs) for fdiv_const with c.
+long long hostsim_check_fdiv_const(float c, unsigned lo_bits, unsigned hi_bits)
+{
+    const float rc = 1.0f / c;
+    long long bad = 0;
+    for (unsigned long long b = lo_bits; b <= hi_bits; b++) {
+        for (int sgn = 0; sgn < 2; sgn++) {
+            const unsigned bits = (unsigned) b | (sgn ? 0x80000000u : 0u);
+            float x;
+            memcpy(&x, &bits, 4);
+            const float q = fdiv_const(x, c, rc), want = x / c;
+            unsigned qb, wb;
+            memcpy(&qb, &q, 4);
+            memcpy(&wb, &want, 4);
+            if (qb != wb && !(q != q && want != want))
+                bad++;
+        }
+    }
+    return bad;
+}
+// 1.0 / sqrt(float) as a double division rounded to float (the reference's normalize_s) equals
+// the float division 1.0f / sqrtf(x): checked over bit patterns [lo_bits, hi_bits].
+long long hostsim_check_rsqrt_identity(unsigned lo_bits, unsigned hi_bits)
+{
+    long long bad = 0;
+    for (unsigned long long b = lo_bits; b <= hi_bits; b++) {
+        float x;
+        const unsigned bits = (unsigned) b;
+        memcpy(&x, &bits, 4);
+        const float r = sqrtf(x);
+        const float viad = (float) (1.0 / (double) r), viaf = 1.0f / r;
+        if (viad != viaf && !(viad != viad && viaf != viaf))
+            bad++;
+    }
+    return bad;
+}
+
 } // extern "C"
