@@ -201,6 +201,13 @@ int validate(rtb200_ctx *ctx, const rtb200_problem *p, unsigned flags)
             return RTB200_ERR_LIMITS;
         }
     }
+    {
+        const rtb200_beam &g = p->seed ? *p->seed_beam : e;
+        if ((long long) g.nx * g.ny >= (1LL << 31) || (long long) g.na * g.nb >= (1LL << 31)) {
+            ctx->err = "more than 2^31 source pixels or angles per pixel";
+            return RTB200_ERR_LIMITS;
+        }
+    }
     if ((p->N - 1) * RTB200_N_SUB > RTB_MAX_SEGS) {
         ctx->err = "too many length segments for the hand-off record";
         return RTB200_ERR_LIMITS;
@@ -315,6 +322,7 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
     long long pix_per_chunk =
         std::max<long long>(1, (long long) (ctx->handoff_bytes / per_slot) / std::max(P.ab_max, 1));
     pix_per_chunk = std::min(pix_per_chunk, pix1 - pix0);
+    pix_per_chunk = std::min<long long>(pix_per_chunk, ((1LL << 31) - 1) / std::max(P.ab_max, 1)); // 32-bit slots
     int rc = ensure_handoff(ctx, pix_per_chunk * P.ab_max, need_exit);
     if (rc)
         return rc;

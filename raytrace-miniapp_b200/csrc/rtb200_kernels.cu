@@ -38,9 +38,16 @@ struct PixelRays {
 __device__ __forceinline__ PixelRays pixel_rays(const DevProblem &P, long long p)
 {
     PixelRays r;
-    r.i = (int) (p % P.snx);
-    r.j = (int) (p / P.snx);
-    const long long AB = (long long) P.sna * P.snb;
+    const unsigned pu = (unsigned) p; // pixel indices fit 32 bits (validated on the host)
+    r.j = (int) (pu / (unsigned) P.snx);
+    r.i = (int) (pu - (unsigned) r.j * (unsigned) P.snx);
+    const int AB32 = P.sna * P.snb;
+    if (P.n_parallel == 1 && P.n_start == 0) { // the common case: every ray of the pixel
+        r.ab0 = 0;
+        r.cnt = AB32;
+        return r;
+    }
+    const long long AB = (long long) AB32;
     const long long base = ((long long) r.i * P.sny + r.j) * AB;
     const long long d = base - P.n_start;
     long long ab0;
@@ -227,8 +234,11 @@ __global__ void __launch_bounds__(128) march_kernel(const DevProblem P, const Ch
 // the next unprocessed slot (one warp-aggregated atomic per refill), so lanes stay busy although
 // the number of steps per ray spans 1..~600 and more than half of the rays of ASE_medium leave
 // the plasma early.
+#ifndef RTB_MARCH_MINBLOCKS
+#define RTB_MARCH_MINBLOCKS 4
+#endif
 template <bool LIST, bool COUNT>
-__global__ void __launch_bounds__(128) march_flat_kernel(const DevProblem P, const Chunk c,
+__global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(const DevProblem P, const Chunk c,
                                                          const Handoff h, FailState *fail,
                                                          unsigned long long *work)
 {
@@ -265,8 +275,9 @@ __global__ void __launch_bounds__(128) march_flat_kernel(const DevProblem P, con
                         const float2 t = __ldg(&c.tans[c.ray0 + L]);
                         rx = r.x, ry = r.y, ra = r.z, rb = r.w, ta = t.x, tb = t.y;
                     } else {
-                        const long long p = phys_pixel(P, c, c.pix0 + L / P.ab_max);
-                        const int t = (int) (L % P.ab_max);
+                        const unsigned lq = (unsigned) L / (unsigned) P.ab_max; // slots fit 32 bits
+                        const long long p = phys_pixel(P, c, c.pix0 + lq);
+                        const int t = (int) ((unsigned) L - lq * (unsigned) P.ab_max);
                         const PixelRays pr = pixel_rays(P, p);
                         active = t < pr.cnt;
                         const int ab = pr.ab0 + t * (int) P.n_parallel;

@@ -90,6 +90,27 @@ inline double host_interp_pchip(size_t N, const double *xi, const double *yi, do
     return f1 + t2 * (2 * t - 3) * (f1 - f2) + t * g1 - t2 * (g1 + (1 - t) * (g1 + g2));
 }
 
+// Interval table of one axis (AxisCell, rtb200_march.cuh): entry k describes [c[k-1], c[k]].
+inline void fill_axis_cells(const double *c, int n, AxisCell *t)
+{
+    std::memset(&t[0], 0, sizeof(AxisCell));
+    for (int k = 1; k < n; k++) {
+        AxisCell a;
+        a.lo = c[k - 1];
+        a.hi = c[k];
+        a.w = c[k] - c[k - 1];
+        a.rw = 1.0 / a.w;
+        a.d = (float) a.w;
+        a.dd = (double) a.d;
+        a.rd = 1.0 / a.dd;
+        a.dm = 0.1f * a.d;
+        const double h = 0.1 * a.w;
+        a.halo_lo = (float) (a.lo - h);
+        a.halo_hi = (float) (a.hi + h);
+        t[k] = a;
+    }
+}
+
 // Bump allocator over the staging blob.  With host == nullptr it only measures.
 class Blob {
 public:
@@ -150,6 +171,8 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
         double *rdx = blob.alloc<double>((size_t) g.Nx, &P.rdx);
         double *rwy = blob.alloc<double>((size_t) g.Ny, &P.rwy);
         double *rdy = blob.alloc<double>((size_t) g.Ny, &P.rdy);
+        AxisCell *cx = blob.alloc<AxisCell>((size_t) g.Nx, &P.cx);
+        AxisCell *cy = blob.alloc<AxisCell>((size_t) g.Ny, &P.cy);
         if (fill) {
             bool ok = true;
             auto recip = [&ok](const double *c, int n, double *rw, double *rd) {
@@ -163,6 +186,8 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
             };
             recip(g.x, g.Nx, rwx, rdx);
             recip(g.y, g.Ny, rwy, rdy);
+            fill_axis_cells(g.x, g.Nx, cx);
+            fill_axis_cells(g.y, g.Ny, cy);
             P.fast_div = ok ? 1 : 0;
             std::memcpy(x, g.x, sizeof(double) * g.Nx);
             std::memcpy(y, g.y, sizeof(double) * g.Ny);
@@ -187,6 +212,10 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
             P.y0 = g.y[0];
             P.inv_dx = g.Nx > 1 ? (double) (g.Nx - 1) / (g.x[g.Nx - 1] - g.x[0]) : 0.0;
             P.inv_dy = g.Ny > 1 ? (double) (g.Ny - 1) / (g.y[g.Ny - 1] - g.y[0]) : 0.0;
+            P.x0f = (float) P.x0;
+            P.y0f = (float) P.y0;
+            P.inv_dxf = (float) P.inv_dx;
+            P.inv_dyf = (float) P.inv_dy;
             planes[ii] = P;
         }
     }

@@ -125,6 +125,15 @@ int hostsim_find_cell(const double *X, int n, double Y)
     return find_cell(X, n, X[0], inv, Y, xl, xr);
 }
 
+int hostsim_find_cell_fast(const double *X, int n, double Yd)
+{
+    std::vector<AxisCell> t((size_t) n);
+    fill_axis_cells(X, n, t.data());
+    const double inv = n > 1 ? (double) (n - 1) / (X[n - 1] - X[0]) : 0.0;
+    const float Yf = (float) Yd; // the march looks up float coordinates
+    return find_cell_fast(t.data(), X, n, (float) X[0], (float) inv, X[0], inv, Yf, (double) Yf);
+}
+
 // FP64 update doors (rtb200_fp64.cuh): the fast exp and the two update branches.
 static const double k_exp_table[64] = { RTB_EXP_TABLE_VALUES };
 static const double k_fp[RTB_K_COUNT] = { RTB_K_VALUES };

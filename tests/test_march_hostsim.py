@@ -27,6 +27,7 @@ def hostsim():
     L.hostsim_pchip.argtypes = [C.c_size_t, abi.c_double_p, abi.c_double_p, C.c_double]
     L.hostsim_get_index.argtypes = [C.c_int, abi.c_double_p, C.c_double, C.c_double]
     L.hostsim_find_cell.argtypes = [abi.c_double_p, C.c_int, C.c_double]
+    L.hostsim_find_cell_fast.argtypes = [abi.c_double_p, C.c_int, C.c_double]
     L.hostsim_tables.argtypes = [C.POINTER(abi.CProblem)] + [C.c_void_p] * 7
     return L
 
@@ -78,6 +79,8 @@ def test_find_cell_equals_reference_bisection(oracle, hostsim):
                                  [np.nan, np.inf, -np.inf]])
             for Y in ys:
                 assert hostsim.hostsim_find_cell(Xp, n, Y) == oracle.L.rt_oracle_findindex(Xp, n, Y), (n, uniform, Y)
+                Yf = float(np.float32(Y))  # the interval-table variant is used on float coordinates
+                assert hostsim.hostsim_find_cell_fast(Xp, n, Y) == oracle.L.rt_oracle_findindex(Xp, n, Yf), (n, uniform, Y)
 
 
 def test_owner_tables_and_seed_factors(seed_small, ase_small, oracle, hostsim):
