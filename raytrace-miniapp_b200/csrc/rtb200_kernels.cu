@@ -305,10 +305,13 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
                 break;
             continue;
         }
-        if (m.phase != PH_DONE) {
-            if (!flat_iterate(m, P.planes, P.N, P.method, P.dz0, P.c, use_emis, sink) ||
-                m.steps > (1u << 22)) {
-                m.phase = PH_DONE;
+        {
+            // every lane takes the trip (finished lanes fall through): see flat_trip
+            const bool was_active = m.phase != PH_DONE;
+            flat_trip(m, P.planes, P.N, P.method, P.dz0, P.c, use_emis, sink);
+            if (was_active && m.steps > (1u << 22))
+                m.phase = PH_DONE; // hang guard: reported as an invalid ray below
+            if (was_active && m.phase == PH_DONE) {
                 unsigned meta = (unsigned) m.seg_lo | ((unsigned) m.seg_hi << 12);
                 if (m.escaped)
                     meta |= RTB_META_ESCAPED;
@@ -831,8 +834,10 @@ __global__ void __launch_bounds__(RTB_FUSED_WARPS * 32, 2)
                 }
                 if (__ballot_sync(0xffffffffu, m.phase != PH_DONE) == 0u)
                     break;
-                if (m.phase != PH_DONE) {
-                    if (!flat_iterate(m, P.planes, P.N, 1, P.dz0, P.c, use_emis, sink)) {
+                {
+                    const bool was_active = m.phase != PH_DONE;
+                    flat_trip(m, P.planes, P.N, 1, P.dz0, P.c, use_emis, sink);
+                    if (was_active && m.phase == PH_DONE) {
                         unsigned meta = (unsigned) m.seg_lo | ((unsigned) m.seg_hi << 12);
                         if (m.escaped)
                             meta |= RTB_META_ESCAPED;
