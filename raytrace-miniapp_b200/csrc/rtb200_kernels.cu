@@ -1073,13 +1073,12 @@ __device__ double dev_calc_seed(const DevProblem &P, double x, double y, double 
     return f < 0.0 ? 0.0 : f;
 }
 
-// One warp per ray slot; K is covered in passes of 64 bins.  Handles both integration modes,
+// One warp per ray slot; K is covered in passes of 32*KS bins (one pass for K <= 128).  Handles both integration modes,
 // both ray sources, scatter binning and the per-ray dumps.
-template <bool LIST>
+template <bool LIST, int KS>
 __global__ void __launch_bounds__(256)
     integrate_scatter_kernel(const DevProblem P, const Chunk c, const Handoff h, const Outputs o)
 {
-    constexpr int KS = 2;
     __shared__ double exp_tab[64];
     load_exp_table(exp_tab);
     const int lane = threadIdx.x & 31;
@@ -1232,10 +1231,21 @@ void launch_integrate_scatter(const DevProblem &P, const Chunk &c, bool list_mod
     const long long cap = 148LL * 8 * 16;
     if (blocks > cap)
         blocks = cap;
-    if (list_mode)
-        integrate_scatter_kernel<true><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, o);
-    else
-        integrate_scatter_kernel<false><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, o);
+    const int ks = std::min(4, (P.K + 31) / 32);
+#define RTB_LAUNCH_SCATTER(KS_)                                                                  \
+    do {                                                                                         \
+        if (list_mode)                                                                           \
+            integrate_scatter_kernel<true, KS_><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, o);  \
+        else                                                                                     \
+            integrate_scatter_kernel<false, KS_><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, o); \
+    } while (0)
+    switch (ks) {
+    case 1: RTB_LAUNCH_SCATTER(1); break;
+    case 2: RTB_LAUNCH_SCATTER(2); break;
+    case 3: RTB_LAUNCH_SCATTER(3); break;
+    default: RTB_LAUNCH_SCATTER(4); break;
+    }
+#undef RTB_LAUNCH_SCATTER
 }
 
 // ------------------------------------------------------------------------------------------
