@@ -639,6 +639,54 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
     return any_neg ? 2 : (any_nan ? 3 : 0);
 }
 
+// Gain-only ray integrator of the seeded path (RayTraceImageHelper.h:569-581):
+//     Iv[k] *= exp( sum over records of (double) gvl * (double) gv[cell][k] ).
+// Records are fetched with one coalesced load per 32 and handed out by shuffles; all lineshape
+// row loads of a ray are independent, so they are in flight together.
+template <int KS>
+__device__ __forceinline__ int integrate_ray_gain_fast(const DevProblem &P, const float *const *s_gv,
+                                                       const SegRec *seg, unsigned meta, int lane,
+                                                       int kbase, double (&Iv)[KS],
+                                                       const ArrayConsts &KC)
+{
+    const int lo = meta & 0xfff, hi = (meta >> 12) & 0xfff;
+    const int K = P.K;
+    int koff[KS];
+    double gl[KS];
+#pragma unroll
+    for (int q = 0; q < KS; q++) {
+        koff[q] = min(kbase + lane + 32 * q, K - 1);
+        gl[q] = 0.0;
+    }
+    for (int c0 = lo; c0 < hi; c0 += 32) {
+        const int cnt = min(32, hi - c0);
+        int4 rv = make_int4(0, 0, 0, 0);
+        if (lane < cnt)
+            rv = __ldg(reinterpret_cast<const int4 *>(&seg[c0 + lane]));
+        for (int j = 0; j < cnt; j++) {
+            const float gvlf = __int_as_float(__shfl_sync(0xffffffffu, rv.x, j));
+            const int cell = __shfl_sync(0xffffffffu, rv.z, j);
+            if (gvlf == 0.0f)
+                continue; // adds exactly +0 to every bin
+            const double gvl = (double) gvlf;
+            const float *row = s_gv[(c0 + j) / RTB_N_SUB + 1] + (size_t) cell * K;
+#pragma unroll
+            for (int q = 0; q < KS; q++)
+                gl[q] = __dadd_rn(gl[q], __dmul_rn(gvl, (double) __ldg(row + koff[q])));
+        }
+    }
+    bool neg = false, nan = false;
+#pragma unroll
+    for (int q = 0; q < KS; q++) {
+        Iv[q] *= exp_any(gl[q], KC);
+        neg = neg || Iv[q] < 0.0;
+        nan = nan || Iv[q] != Iv[q];
+    }
+    const bool any_neg = __any_sync(0xffffffffu, neg);
+    const bool any_nan = __any_sync(0xffffffffu, nan);
+    return any_neg ? 2 : (any_nan ? 3 : 0);
+}
+
 #define RTB_OWNER_WARPS 8
 #ifndef RTB_OWNER_MINBLOCKS
 #define RTB_OWNER_MINBLOCKS 3
@@ -978,25 +1026,28 @@ bool launch_trace_ase_fused(const DevProblem &P, long long pix0, long long pix1,
     return true;
 }
 
-// getIndex (RayTraceImageCPU.cpp:11-16) on the device, for the exit ray.
+// getIndex (RayTraceImageCPU.cpp:11-16) on the device, for the exit ray: -1 outside the grid
+// +- half a cell, else findfirstsingle(x, n, y - dx/2) = the first index with x[idx] >= Y
+// (0 below the grid, n above it).  The euv grids are uniform (validated), so the index is
+// guessed in closed form and then fixed up against the real coordinates: the result is the
+// reference's bisection result for any monotone grid.
 __device__ __forceinline__ int dev_get_index(int n, const double *x, double dx, double y)
 {
-    if (y < __ldg(&x[0]) - 0.5 * dx || y > __ldg(&x[n - 1]) + 0.5 * dx)
+    const double x0 = __ldg(&x[0]), xn = __ldg(&x[n - 1]);
+    if (y < x0 - 0.5 * dx || y > xn + 0.5 * dx)
         return -1;
     const double Y = y - 0.5 * dx;
-    if (Y < __ldg(&x[0]))
+    if (Y < x0)
         return 0;
-    if (Y > __ldg(&x[n - 1]))
+    if (Y > xn)
         return n;
-    int lo = 0, hi = n - 1;
-    while (hi - lo != 1) {
-        const int mid = (hi + lo) / 2;
-        if (__ldg(&x[mid]) >= Y)
-            hi = mid;
-        else
-            lo = mid;
-    }
-    return hi;
+    int k = (int) ceil((Y - x0) / dx); // guess
+    k = k < 0 ? 0 : (k > n - 1 ? n - 1 : k);
+    while (k > 0 && __ldg(&x[k - 1]) >= Y)
+        --k;
+    while (k < n - 1 && !(__ldg(&x[k]) >= Y))
+        ++k;
+    return k;
 }
 
 // findfirstsingle / interp_pchip / calc_seed_inline (RayTraceImageHelper.h:101-117, :168-247)
@@ -1079,15 +1130,57 @@ template <bool LIST, int KS>
 __global__ void __launch_bounds__(256)
     integrate_scatter_kernel(const DevProblem P, const Chunk c, const Handoff h, const Outputs o)
 {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double exp_tab[64];
-    load_exp_table(exp_tab);
+    const float **s_gv = reinterpret_cast<const float **>(smem_raw); // [N] gv base pointers
+    for (int i = threadIdx.x; i < P.N; i += blockDim.x)
+        s_gv[i] = P.planes[i].gv;
+    load_exp_table(exp_tab); // includes __syncthreads()
+    const ArrayConsts KC{ P.kfp, exp_tab };
+    const bool gain_only = P.use_emis == 0;
     const int lane = threadIdx.x & 31;
     const long long warp_id = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long) gridDim.x * blockDim.x) >> 5;
     const long long n_slots = LIST ? (c.ray1 - c.ray0) : (c.pix1 - c.pix0) * P.ab_max;
     const int S = (P.N - 1) * RTB_N_SUB;
     const int K = P.K;
-    for (long long slot = warp_id; slot < n_slots; slot += n_warps) {
+    // Each warp takes RUN consecutive ray slots at a time.  Consecutive rays (b fastest, then a)
+    // leave the plasma next to each other, so they mostly fall into the same image pixel and
+    // the same angular bin: their contributions are summed in registers and flushed with one
+    // set of FP64 atomics when the destination changes, instead of 1 + K atomics per ray onto
+    // addresses that thousands of concurrent rays share (measured: the atomics, not the
+    // arithmetic, bound the seeded path, profiles/r01_seed).
+    constexpr int RUN = 64;
+    double acc[KS];
+#pragma unroll
+    for (int q = 0; q < KS; q++)
+        acc[q] = 0.0;
+    double acc_w = 0.0;
+    long long cur_pix = -1;
+    int cur_bin = -1;
+    const bool combine = K <= 32 * KS; // single pass over the bins
+    auto flush_pix = [&]() {
+        if (cur_pix >= 0) {
+#pragma unroll
+            for (int q = 0; q < KS; q++) {
+                const int k = lane + 32 * q;
+                if (k < K)
+                    atomicAdd(&o.image[(size_t) K * (size_t) cur_pix + k], acc[q]);
+                acc[q] = 0.0;
+            }
+        }
+        cur_pix = -1;
+    };
+    auto flush_bin = [&]() {
+        if (cur_bin >= 0 && lane == 0)
+            atomicAdd(&o.I_ang[cur_bin], acc_w);
+        acc_w = 0.0;
+        cur_bin = -1;
+    };
+    const long long n_runs = (n_slots + RUN - 1) / RUN;
+    for (long long run = warp_id; run < n_runs; run += n_warps) {
+    const long long slot_end = (run + 1) * RUN < n_slots ? (run + 1) * RUN : n_slots;
+    for (long long slot = run * RUN; slot < slot_end; slot++) {
         const unsigned meta = __ldg(&h.meta[slot]);
         if (meta & RTB_META_INACTIVE)
             continue;
@@ -1154,7 +1247,9 @@ __global__ void __launch_bounds__(256)
                 Iv[q] = (f != 0.0 && k < K) ? __dmul_rn(f, __ldg(&P.seed_fv[k])) : 0.0;
             }
             if (!invalid) {
-                const int cc = integrate_ray<KS>(P, h.seg + slot * S, meta, lane, kbase, Iv, exp_tab);
+                const int cc = gain_only
+                                   ? integrate_ray_gain_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, kbase, Iv, KC)
+                                   : integrate_ray<KS>(P, h.seg + slot * S, meta, lane, kbase, Iv, exp_tab);
                 if (cc != 0) {
                     code = code == 0 ? cc : (cc < code ? cc : code); // negative (2) wins over NaN (3)
                 }
@@ -1169,16 +1264,20 @@ __global__ void __launch_bounds__(256)
             }
             // Binning is deferred until the whole ray is known to be valid when K needs
             // several passes; with one pass (K <= 64) it happens right here.
-            if (K <= 32 * KS) {
+            if (combine) {
                 if (code == 0 && !invalid) {
+                    const long long pix = (o.image && i1 >= 0 && i2 >= 0)
+                                              ? (long long) i1 + (long long) i2 * P.nx : -1;
+                    if (pix != cur_pix) {
+                        flush_pix();
+                        cur_pix = pix;
+                    }
 #pragma unroll
                     for (int q = 0; q < KS; q++) {
                         const int k = lane + 32 * q;
                         if (k < K) {
                             w += __ldg(&P.dv2[k]) * Iv[q];
-                            if (o.image && i1 >= 0 && i2 >= 0)
-                                atomicAdd(&o.image[(size_t) K * ((size_t) i1 + (size_t) i2 * P.nx) + k],
-                                          Iv[q] * P.scale);
+                            acc[q] += Iv[q] * P.scale;
                         }
                     }
                 }
@@ -1193,7 +1292,10 @@ __global__ void __launch_bounds__(256)
                     const int k = kbase + lane + 32 * q;
                     Iv[q] = (f != 0.0 && k < K) ? __dmul_rn(f, __ldg(&P.seed_fv[k])) : 0.0;
                 }
-                integrate_ray<KS>(P, h.seg + slot * S, meta, lane, kbase, Iv, exp_tab);
+                if (gain_only)
+                    integrate_ray_gain_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, kbase, Iv, KC);
+                else
+                    integrate_ray<KS>(P, h.seg + slot * S, meta, lane, kbase, Iv, exp_tab);
 #pragma unroll
                 for (int q = 0; q < KS; q++) {
                     const int k = kbase + lane + 32 * q;
@@ -1208,8 +1310,12 @@ __global__ void __launch_bounds__(256)
         }
         if (code == 0 && !invalid && o.I_ang) {
             w = warp_sum(w);
-            if (lane == 0 && i3 >= 0 && i4 >= 0)
-                atomicAdd(&o.I_ang[i3 + i4 * P.na], w);
+            const int bin = (i3 >= 0 && i4 >= 0) ? i3 + i4 * P.na : -1;
+            if (bin != cur_bin) {
+                flush_bin();
+                cur_bin = bin;
+            }
+            acc_w += w;
         }
         if (lane == 0) {
             if (o.error)
@@ -1217,6 +1323,9 @@ __global__ void __launch_bounds__(256)
             if (code >= 2)
                 report_failure(o.fail, code, rx, ry, ra, rb);
         }
+    }
+    flush_pix();
+    flush_bin();
     }
 }
 
@@ -1232,12 +1341,13 @@ void launch_integrate_scatter(const DevProblem &P, const Chunk &c, bool list_mod
     if (blocks > cap)
         blocks = cap;
     const int ks = std::min(4, (P.K + 31) / 32);
+    const size_t smem = sizeof(float *) * (size_t) P.N;
 #define RTB_LAUNCH_SCATTER(KS_)                                                                  \
     do {                                                                                         \
         if (list_mode)                                                                           \
-            integrate_scatter_kernel<true, KS_><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, o);  \
+            integrate_scatter_kernel<true, KS_><<<(unsigned) blocks, threads, smem, st>>>(P, c, h, o);  \
         else                                                                                     \
-            integrate_scatter_kernel<false, KS_><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, o); \
+            integrate_scatter_kernel<false, KS_><<<(unsigned) blocks, threads, smem, st>>>(P, c, h, o); \
     } while (0)
     switch (ks) {
     case 1: RTB_LAUNCH_SCATTER(1); break;
