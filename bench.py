@@ -272,6 +272,12 @@ def run_gpu(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["integrate_ase_owner_kernel"]
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            pass
         launches_integ = max(1, launches_per_step // 2) * K
         integ_s = integ_ms * 1e-3
         upd_local = W_upd / world  # per rank (weak: identical tiles)
@@ -299,7 +305,9 @@ def run_gpu(args):
             "roofline": {
                 "bound": "fp64", "kernel": "integrate_ase_owner_kernel",
                 "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-                "frac": achieved_tflops / peak_tflops, "traffic": None,
+                "frac": achieved_tflops / peak_tflops, "traffic": traffic,
+                "traffic_note": "dram read+write bytes per launch (ncu, profiles/r01_traffic.json): the "
+                                "march->integrate hand-off records, not re-reads of the inputs",
                 "convention": "%d FP64 instr per frequency update (SURVEY.md 8d) x 2 flop; peak = "
                               "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has "
                               "no FP64 entry)" % FP64_INSTR_PER_UPDATE,
