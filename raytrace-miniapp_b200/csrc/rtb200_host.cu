@@ -120,7 +120,7 @@ struct rtb200_ctx {
     bool use_fused = false; // opt-in (RTB200_FUSED=1): measured slower than the two-kernel path
     bool flat_march = true;
     unsigned long long *d_work = nullptr;
-    size_t handoff_bytes = 256u << 20;
+    size_t handoff_bytes = (size_t) 4096 << 20; // B200 has 180 GB: one chunk for every shipped / synthetic size
 };
 
 namespace {

@@ -568,47 +568,64 @@ template <int KS>
 __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const float *const *s_gv,
                                                       const SegRec *seg, unsigned meta, int lane,
                                                       const int (&koff)[KS], double (&Iv)[KS],
-                                                      const PinnedConsts &KC)
+                                                      const PinnedConsts &KC, uint4 *slab)
 {
     const int lo = meta & 0xfff, hi = (meta >> 12) & 0xfff;
     const int K = P.K;
     for (int c0 = lo; c0 < hi; c0 += 32) {
         const int cnt = min(32, hi - c0);
-        int4 rv = make_int4(0, 0, 0, 0);
-        if (lane < cnt)
-            rv = __ldg(reinterpret_cast<const int4 *>(&seg[c0 + lane]));
+        // Lane j fetches record c0 + j (one coalesced 16-byte load per lane) and resolves the
+        // address of its lineshape row; the warp then walks the records through its
+        // shared-memory slab: one 16-byte broadcast read per record replaces three shuffles,
+        // the plane look-up and the 64-bit address arithmetic.
+        __syncwarp();
+        if (lane < cnt) {
+            const int4 rv = __ldg(reinterpret_cast<const int4 *>(&seg[c0 + lane]));
+            const float *row = s_gv[(c0 + lane) / RTB_N_SUB + 1] + (size_t) rv.z * K;
+            const unsigned long long ra = reinterpret_cast<unsigned long long>(row);
+            slab[lane] = make_uint4((unsigned) rv.x, (unsigned) rv.y, (unsigned) ra, (unsigned) (ra >> 32));
+        }
+        __syncwarp();
+        uint4 e = slab[0];
         float gn[KS];
         {
-            const float *row = s_gv[c0 / RTB_N_SUB + 1] + (size_t) __shfl_sync(0xffffffffu, rv.z, 0) * K;
+            const float *row = reinterpret_cast<const float *>(((unsigned long long) e.w << 32) | e.z);
 #pragma unroll
             for (int q = 0; q < KS; q++)
                 gn[q] = __ldg(row + koff[q]);
         }
         for (int j = 0; j < cnt; j++) {
-            const float gvl = __int_as_float(__shfl_sync(0xffffffffu, rv.x, j));
-            const float evl = __int_as_float(__shfl_sync(0xffffffffu, rv.y, j));
+            const float gvl = __uint_as_float(e.x), evl = __uint_as_float(e.y);
             float g[KS];
 #pragma unroll
             for (int q = 0; q < KS; q++)
                 g[q] = gn[q];
-            if (j + 1 < cnt) {
-                const float *row = s_gv[(c0 + j + 1) / RTB_N_SUB + 1] +
-                                   (size_t) __shfl_sync(0xffffffffu, rv.z, j + 1) * K;
+            if (j + 1 < cnt) { // request the next record's row before integrating this one
+                e = slab[j + 1];
+                const float *row = reinterpret_cast<const float *>(((unsigned long long) e.w << 32) | e.z);
 #pragma unroll
                 for (int q = 0; q < KS; q++)
                     gn[q] = __ldg(row + koff[q]);
             }
             if (gvl == 0.0f && evl == 0.0f)
                 continue; // gl = el = 0: the update is the identity
+            // One warp-wide OR gathers every branch decision of the record: bit 2q = "some lane
+            // of slot q takes the Taylor branch", bit 2q+1 = "some lane takes the exp branch",
+            // bit 31 = "some |gl| >= 700, inf or NaN" (library semantics).
             float glf[KS], elf[KS];
-            bool odd = false;
+            bool small[KS];
+            unsigned flags = 0u;
 #pragma unroll
             for (int q = 0; q < KS; q++) {
                 glf[q] = __fmul_rn(gvl, g[q]);
                 elf[q] = __fmul_rn(evl, g[q]);
-                odd = odd || !(fabsf(glf[q]) < 700.0f);
+                const float ag = fabsf(glf[q]);
+                small[q] = ag < 1e-3f; // == (fabs((double) glf) < 1e-3)
+                flags |= (small[q] ? 1u : 2u) << (2 * q);
+                flags |= !(ag < 700.0f) ? 0x80000000u : 0u;
             }
-            if (__any_sync(0xffffffffu, odd)) { // |gl| >= 700, inf or NaN: library semantics
+            flags = __reduce_or_sync(0xffffffffu, flags);
+            if (flags & 0x80000000u) {
 #pragma unroll
                 for (int q = 0; q < KS; q++)
                     Iv[q] = ase_update_library(Iv[q], (double) glf[q], (double) elf[q]);
@@ -616,15 +633,13 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
             }
 #pragma unroll
             for (int q = 0; q < KS; q++) {
-                const bool small = fabsf(glf[q]) < 1e-3f; // == (fabs((double) glf) < 1e-3)
-                const unsigned b_small = __ballot_sync(0xffffffffu, small);
                 const double gl = (double) glf[q], el = (double) elf[q];
                 double a = 0.0, b = 0.0;
-                if (b_small != 0u) // warp-uniform: some lane takes the Taylor branch
+                if (flags & (1u << (2 * q))) // warp-uniform
                     a = ase_update_small(Iv[q], gl, el, KC);
-                if (b_small != 0xffffffffu) // warp-uniform: some lane takes the exp branch
+                if (flags & (2u << (2 * q))) // warp-uniform
                     b = ase_update_large(Iv[q], gl, el, rcp_approx(glf[q]), KC);
-                Iv[q] = small ? a : b;
+                Iv[q] = small[q] ? a : b;
             }
         }
     }
@@ -699,6 +714,7 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, RTB_OWNER_MINBLOCKS)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double part[RTB_OWNER_WARPS][KS * 32];
     __shared__ double exp_tab[64];
+    __shared__ uint4 rec_slab[RTB_OWNER_WARPS][32]; // per-warp record + row-address slab
     const float **s_gv = reinterpret_cast<const float **>(smem_raw); // [N] gv base pointers
     for (int i = threadIdx.x; i < P.N; i += blockDim.x)
         s_gv[i] = P.planes[i].gv;
@@ -729,7 +745,8 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, RTB_OWNER_MINBLOCKS)
         for (int q = 0; q < KS; q++)
             Iv[q] = 0.0;
         const int code =
-            integrate_ray_ase_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, koff, Iv, KC);
+            integrate_ray_ase_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, koff, Iv, KC,
+                                       rec_slab[warp]);
         const int ab = pr.ab0 + t * (int) P.n_parallel;
         const int ka = ab / P.snb, m = ab % P.snb;
         if (code != 0) {
