@@ -547,7 +547,9 @@ struct PinnedConsts {
         c4_ = pin(kc + RTB_K_C4);
         c3_ = pin(kc + RTB_K_C3);
         third_ = pin(kc + RTB_K_THIRD);
-        tab_ = (unsigned) __cvta_generic_to_shared(T);
+        // the shuffle makes the shared-memory address opaque: otherwise the compiler rebuilds it
+        // from the CTA's shared window (4 uniform-datapath instructions) at every use
+        tab_ = __shfl_sync(0xffffffffu, (unsigned) __cvta_generic_to_shared(T), 0);
     }
     __device__ __forceinline__ double l2e() const { return l2e_; }
     __device__ __forceinline__ double hi() const { return hi_; }
@@ -568,10 +570,18 @@ template <int KS>
 __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const float *const *s_gv,
                                                       const SegRec *seg, unsigned meta, int lane,
                                                       const int (&koff)[KS], double (&Iv)[KS],
-                                                      const PinnedConsts &KC, uint4 *slab)
+                                                      const PinnedConsts &KC, unsigned slab)
 {
+    // slab: shared-space address of this warp's 32 x 16-byte record slab (opaque register)
     const int lo = meta & 0xfff, hi = (meta >> 12) & 0xfff;
     const int K = P.K;
+    auto slab_load = [slab](int j) {
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"(slab + 16u * (unsigned) j));
+        return v;
+    };
     for (int c0 = lo; c0 < hi; c0 += 32) {
         const int cnt = min(32, hi - c0);
         // Lane j fetches record c0 + j (one coalesced 16-byte load per lane) and resolves the
@@ -583,10 +593,13 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
             const int4 rv = __ldg(reinterpret_cast<const int4 *>(&seg[c0 + lane]));
             const float *row = s_gv[(c0 + lane) / RTB_N_SUB + 1] + (size_t) rv.z * K;
             const unsigned long long ra = reinterpret_cast<unsigned long long>(row);
-            slab[lane] = make_uint4((unsigned) rv.x, (unsigned) rv.y, (unsigned) ra, (unsigned) (ra >> 32));
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slab + 16u * (unsigned) lane),
+                         "r"((unsigned) rv.x), "r"((unsigned) rv.y), "r"((unsigned) ra),
+                         "r"((unsigned) (ra >> 32))
+                         : "memory");
         }
         __syncwarp();
-        uint4 e = slab[0];
+        uint4 e = slab_load(0);
         float gn[KS];
         {
             const float *row = reinterpret_cast<const float *>(((unsigned long long) e.w << 32) | e.z);
@@ -601,7 +614,7 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
             for (int q = 0; q < KS; q++)
                 g[q] = gn[q];
             if (j + 1 < cnt) { // request the next record's row before integrating this one
-                e = slab[j + 1];
+                e = slab_load(j + 1);
                 const float *row = reinterpret_cast<const float *>(((unsigned long long) e.w << 32) | e.z);
 #pragma unroll
                 for (int q = 0; q < KS; q++)
@@ -735,6 +748,8 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, RTB_OWNER_MINBLOCKS)
         koff[q] = min(k, K - 1); // lanes past the last bin recompute bin K-1 (never stored)
     }
     const PinnedConsts KC(P.kfp_g, exp_tab);
+    const unsigned slab_addr =
+        __shfl_sync(0xffffffffu, (unsigned) __cvta_generic_to_shared(&rec_slab[warp][0]), 0);
     for (int t = warp; t < pr.cnt; t += RTB_OWNER_WARPS) {
         const long long slot = slot0 + t;
         const unsigned meta = __ldg(&h.meta[slot]);
@@ -745,8 +760,7 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, RTB_OWNER_MINBLOCKS)
         for (int q = 0; q < KS; q++)
             Iv[q] = 0.0;
         const int code =
-            integrate_ray_ase_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, koff, Iv, KC,
-                                       rec_slab[warp]);
+            integrate_ray_ase_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, koff, Iv, KC, slab_addr);
         const int ab = pr.ab0 + t * (int) P.n_parallel;
         const int ka = ab / P.snb, m = ab % P.snb;
         if (code != 0) {
