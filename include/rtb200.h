@@ -143,6 +143,18 @@ int rtb200_calc_rays(rtb200_ctx *ctx, int N, double dz, const rtb200_gain_plane 
                      size_t n_rays, double *Iv, rtb200_ray *ray2, int *error, float *gvl,
                      float *evl, int32_t *ivl);
 
+/* Replaces RayTrace::calc_ray_path (src/RayTrace.h:69-72, src/RayTraceImage.cpp:440-477; the
+ * RAY_DEBUG path of RayTrace_calc_ray, src/common/RayTraceImageHelper.h:419-426, :505-511,
+ * :536-566): the trajectory of every ray.  xr, yr, Ir are [n_rays][N_SUB*(N-1)+1] floats in the
+ * order of `rays` (position at every sub-segment boundary, intensity sum_k 2*Iv[k]*dv[k] after
+ * every sub-segment; emission-style integration as the reference does whenever it records a
+ * trajectory); error[n_rays] = 0, -1, -2, -3.  c = step safety factor (0.5 in create_image).
+ * K <= 128.  Returns RTB200_RAYS_FAILED when any ray failed (the reference returns the count). */
+int rtb200_calc_ray_paths(rtb200_ctx *ctx, int N, double dz, const rtb200_gain_plane *gain,
+                          const rtb200_seed *seed, int K, const double *dv, int method, double c,
+                          const rtb200_ray *rays, size_t n_rays, float *xr, float *yr, float *Ir,
+                          int *error);
+
 /* ---- the path, device-resident (for throughput measurement and multi-GPU tiling) ----------- */
 
 /* Upload + re-layout the problem into the context's device arena (one packed SoA blob, one

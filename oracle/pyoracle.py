@@ -58,6 +58,11 @@ class Oracle:
                                          C.c_int, C.c_float, abi.c_double_p, C.POINTER(abi.Ray),
                                          abi.c_float_p, abi.c_float_p, C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+        L.rt_oracle_calc_ray_debug.restype = C.c_int
+        L.rt_oracle_calc_ray_debug.argtypes = [C.POINTER(abi.Ray), C.c_int, C.c_float,
+                                               C.POINTER(abi.GainPlane), C.POINTER(abi.Seed),
+                                               C.c_int, C.c_int, C.c_float, abi.c_double_p,
+                                               abi.c_double_p, C.POINTER(abi.Ray), abi.c_float_p]
         L.rt_oracle_trace_rays.restype = None
         L.rt_oracle_trace_rays.argtypes = [C.c_int, C.POINTER(abi.Beam), C.POINTER(abi.GainPlane),
                                            C.POINTER(abi.Seed), C.c_int, C.POINTER(abi.Ray),
@@ -146,6 +151,28 @@ class Oracle:
             esc[i] = e_.value
         return dict(Iv=Iv, ray2=ray2, error=err, gvl=gvl, evl=evl, ivl=ivl, escaped=esc,
                     steps=steps.value)
+
+
+    def calc_ray_paths(self, problem, rays, method=None, c=0.5):
+        """RAY_DEBUG trajectories: (x, y, I)[n_rays, N_SUB*(N-1)+1] and the error codes."""
+        rays = np.ascontiguousarray(rays, abi.ray_dtype)
+        n, N, K = rays.size, problem.N, problem.euv_beam.nv
+        method = problem.method if method is None else method
+        planes = (abi.GainPlane * N)(*[g.c_struct() for g in problem.gain])
+        sd = problem.seed.c_struct() if problem.seed is not None else None
+        N2 = abi.N_SUB * (N - 1) + 1
+        dbg = np.zeros((n, N2, 3), np.float32)
+        err = np.zeros(n, np.int32)
+        Iv = np.zeros(K)
+        r2 = abi.Ray()
+        rp = _ptr(rays, abi.Ray)
+        dv = np.ascontiguousarray(problem.euv_beam.dv)
+        for i in range(n):
+            err[i] = self.L.rt_oracle_calc_ray_debug(
+                C.byref(rp[i]), N, np.float32(problem.euv_beam.dz), planes,
+                C.byref(sd) if sd else None, K, method, c, _ptr(dv, C.c_double),
+                _ptr(Iv, C.c_double), C.byref(r2), _ptr(dbg[i], C.c_float))
+        return dict(x=dbg[:, :, 0].copy(), y=dbg[:, :, 1].copy(), I=dbg[:, :, 2].copy(), error=err)
 
 
 class Reference:

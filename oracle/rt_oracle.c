@@ -224,10 +224,10 @@ static float propagate2(vec3f *pos, vec3f *s, float dz, const double x[2], const
 /* src/common/RayTraceImageHelper.h:379-595 (RayTrace_calc_ray, non-debug path).
  * gvl/evl/ivl are [(N-1)*N_SUB] in the reference's [i][is] order (caller scratch, may be
  * inspected afterwards).  Returns 0, -1, -2 or -3 like the reference. */
-int rt_oracle_calc_ray(const rtb200_ray *ray, int N, float dz0, const rtb200_gain_plane *gain,
-                       const rtb200_seed *seed, int K, int method, float c, double *Iv,
-                       rtb200_ray *ray2, float *gvl, float *evl, int32_t *ivl,
-                       int *escaped_out, uint64_t *steps)
+static int calc_ray_impl(const rtb200_ray *ray, int N, float dz0, const rtb200_gain_plane *gain,
+                         const rtb200_seed *seed, int K, int method, float c, double *Iv,
+                         rtb200_ray *ray2, float *gvl, float *evl, int32_t *ivl,
+                         int *escaped_out, uint64_t *steps, const double *dv, float *debug)
 {
     const int S = (N - 1) * N_SUB;
     for (int i = 0; i < S; i++) {
@@ -253,6 +253,12 @@ int rt_oracle_calc_ray(const rtb200_ray *ray, int N, float dz0, const rtb200_gai
         s.z = -s.z;
     }
     normalize_s(&s);
+    if (dv != NULL && debug != NULL) { /* RAY_DEBUG, :419-426 */
+        int ii = method == 1 ? (N - 1) * N_SUB : 0;
+        memset(debug, 0, 3 * (size_t) (N_SUB * (N - 1) + 1) * sizeof(float));
+        debug[3 * ii + 0] = pos.x;
+        debug[3 * ii + 1] = pos.y;
+    }
 
     int escaped = 0;
     for (int i = 0; i < N - 1 && !escaped; i++) { /* :430 */
@@ -317,6 +323,11 @@ int rt_oracle_calc_ray(const rtb200_ray *ray, int N, float dz0, const rtb200_gai
                 evl[idx] += E0 * ds_sum;
                 ivl[idx] = (int32_t) i1;
             }
+            if (dv != NULL && debug != NULL) { /* :505-511 */
+                int index = N_SUB * (ii - 1) + is + (method == 1 ? 0 : 1);
+                debug[3 * index + 0] = pos.x;
+                debug[3 * index + 1] = pos.y;
+            }
         }
     }
     if (escaped_out)
@@ -334,7 +345,12 @@ int rt_oracle_calc_ray(const rtb200_ray *ray, int N, float dz0, const rtb200_gai
     } else if (method == 2) {
         rt_oracle_calc_seed(seed, ray->x, ray->y, ray->a, ray->b, Iv);
     }
-    if (use_emis) { /* :543-568 */
+    if (dv != NULL && debug != NULL) { /* :536-542 */
+        debug[2] = 0.0f;
+        for (int k = 0; k < K; k++)
+            debug[2] += (float) (2 * Iv[k] * dv[k]);
+    }
+    if (use_emis || debug != NULL) { /* :543-568 */
         for (int i = 0; i < N - 1; i++) {
             for (int is = 0; is < N_SUB; is++) {
                 const float *gv = &gain[i + 1].gv[(size_t) ivl[i * N_SUB + is] * (size_t) K];
@@ -349,6 +365,12 @@ int rt_oracle_calc_ray(const rtb200_ray *ray, int N, float dz0, const rtb200_gai
                         double exp_gl = exp(gl);
                         Iv[k] = el / gl * (exp_gl - 1.0) + Iv[k] * exp_gl;
                     }
+                }
+                if (dv != NULL && debug != NULL) { /* :559-566 */
+                    int index = 3 * (N_SUB * i + is + 1) + 2;
+                    debug[index] = 0.0f;
+                    for (int k = 0; k < K; k++)
+                        debug[index] += (float) (2 * Iv[k] * dv[k]);
                 }
             }
         }
@@ -370,6 +392,36 @@ int rt_oracle_calc_ray(const rtb200_ray *ray, int N, float dz0, const rtb200_gai
         nans = nans || Iv[jj] != Iv[jj];
     }
     return neg ? -2 : (nans ? -3 : 0);
+}
+
+int rt_oracle_calc_ray(const rtb200_ray *ray, int N, float dz0, const rtb200_gain_plane *gain,
+                       const rtb200_seed *seed, int K, int method, float c, double *Iv,
+                       rtb200_ray *ray2, float *gvl, float *evl, int32_t *ivl,
+                       int *escaped_out, uint64_t *steps)
+{
+    return calc_ray_impl(ray, N, dz0, gain, seed, K, method, c, Iv, ray2, gvl, evl, ivl,
+                         escaped_out, steps, NULL, NULL);
+}
+
+/* RayTrace_calc_ray with dv and debug given (the RAY_DEBUG trajectory used by
+ * RayTrace::calc_ray_path, src/RayTraceImage.cpp:440-477): debug[3*n + 0..2] = x, y, I at the
+ * n-th sub-segment boundary, n = 0 .. N_SUB*(N-1).  Note that with debug != NULL the reference
+ * always takes the emission-style integration (:543). */
+int rt_oracle_calc_ray_debug(const rtb200_ray *ray, int N, float dz0,
+                             const rtb200_gain_plane *gain, const rtb200_seed *seed, int K,
+                             int method, float c, const double *dv, double *Iv, rtb200_ray *ray2,
+                             float *debug)
+{
+    const int S = (N - 1) * N_SUB;
+    float *gvl = (float *) malloc(sizeof(float) * (size_t) (S > 0 ? S : 1));
+    float *evl = (float *) malloc(sizeof(float) * (size_t) (S > 0 ? S : 1));
+    int32_t *ivl = (int32_t *) malloc(sizeof(int32_t) * (size_t) (S > 0 ? S : 1));
+    int rc = calc_ray_impl(ray, N, dz0, gain, seed, K, method, c, Iv, ray2, gvl, evl, ivl, NULL,
+                           NULL, dv, debug);
+    free(gvl);
+    free(evl);
+    free(ivl);
+    return rc;
 }
 
 /* src/RayTraceImageCPU.cpp:11-16 */

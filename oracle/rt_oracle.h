@@ -25,6 +25,11 @@ int rt_oracle_calc_ray(const rtb200_ray *ray, int N, float dz0, const rtb200_gai
                        rtb200_ray *ray2, float *gvl, float *evl, int32_t *ivl,
                        int *escaped_out, uint64_t *steps);
 
+int rt_oracle_calc_ray_debug(const rtb200_ray *ray, int N, float dz0,
+                             const rtb200_gain_plane *gain, const rtb200_seed *seed, int K,
+                             int method, float c, const double *dv, double *Iv, rtb200_ray *ray2,
+                             float *debug);
+
 void rt_oracle_trace_rays(int N, const rtb200_beam *beam, const rtb200_gain_plane *gain,
                           const rtb200_seed *seed, int method, const rtb200_ray *rays,
                           size_t n_rays, double scale, double *image, double *I_ang,

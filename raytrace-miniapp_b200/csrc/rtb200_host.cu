@@ -105,6 +105,8 @@ struct rtb200_ctx {
     DevBuf<int> d_err;
     DevBuf<float4> d_rays;
     DevBuf<float2> d_tans;
+    DevBuf<float2> d_path_xy;
+    DevBuf<float> d_path_I;
     PinBuf h_out;
     FailState *d_fail = nullptr;
     FailState *h_fail = nullptr; // pinned
@@ -326,7 +328,7 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
     int rc = ensure_handoff(ctx, pix_per_chunk * P.ab_max, need_exit);
     if (rc)
         return rc;
-    Handoff h{ ctx->d_seg.p, ctx->d_meta.p, need_exit ? ctx->d_exit.p : nullptr };
+    Handoff h{ ctx->d_seg.p, ctx->d_meta.p, need_exit ? ctx->d_exit.p : nullptr, nullptr };
     for (long long a = pix0; a < pix1; a += pix_per_chunk) {
         Chunk c;
         std::memset(&c, 0, sizeof(c));
@@ -457,6 +459,8 @@ void rtb200_destroy(rtb200_ctx *ctx)
     ctx->d_err.release();
     ctx->d_rays.release();
     ctx->d_tans.release();
+    ctx->d_path_xy.release();
+    ctx->d_path_I.release();
     ctx->h_out.release();
     if (ctx->d_fail)
         cudaFree(ctx->d_fail);
@@ -665,7 +669,7 @@ int launch_list(rtb200_ctx *ctx, size_t n_rays, const Outputs &out_all, bool kee
     int rc = ensure_handoff(ctx, per_chunk, true);
     if (rc)
         return rc;
-    Handoff h{ ctx->d_seg.p, ctx->d_meta.p, ctx->d_exit.p };
+    Handoff h{ ctx->d_seg.p, ctx->d_meta.p, ctx->d_exit.p, nullptr };
     for (long long a = 0; a < (long long) n_rays; a += per_chunk) {
         Chunk c;
         std::memset(&c, 0, sizeof(c));
@@ -846,6 +850,95 @@ int rtb200_calc_rays(rtb200_ctx *ctx, int N, double dz, const rtb200_gain_plane 
         }
     }
     return RTB200_OK;
+}
+
+int rtb200_calc_ray_paths(rtb200_ctx *ctx, int N, double dz, const rtb200_gain_plane *gain,
+                          const rtb200_seed *seed, int K, const double *dv, int method, double c,
+                          const rtb200_ray *rays, size_t n_rays, float *xr, float *yr, float *Ir,
+                          int *error)
+{
+    if (!ctx || !gain || !dv || (n_rays && !rays) || (method != 1 && method != 2) || K < 1 ||
+        N < 1 || (N - 1) * RTB200_N_SUB > RTB_MAX_SEGS) {
+        if (ctx)
+            ctx->err = "rtb200_calc_ray_paths: bad argument";
+        return RTB200_ERR_ARG;
+    }
+    if (K > 128) {
+        ctx->err = "rtb200_calc_ray_paths: more than 128 frequencies";
+        return RTB200_ERR_LIMITS;
+    }
+    for (int i = 0; i < N; i++)
+        if (gain[i].Nx < 2 || gain[i].Ny < 2 || gain[i].Nv != K) {
+            ctx->err = "rtb200_calc_ray_paths: invalid gain plane";
+            return RTB200_ERR_ARG;
+        }
+    rtb200_beam beam;
+    std::memset(&beam, 0, sizeof(beam));
+    beam.nv = K;
+    beam.dz = dz;
+    beam.dv = dv;
+    rtb200_problem p;
+    std::memset(&p, 0, sizeof(p));
+    p.N = N;
+    p.N_parallel = 1;
+    p.euv_beam = &beam;
+    p.gain = gain;
+    p.seed = seed;
+    reset_timing(ctx);
+    new_event(ctx, ctx->stream);
+    int rc = stage_impl(ctx, &p, true, method, 1.0);
+    if (rc)
+        return rc;
+    ctx->prob.c = (float) c;
+    if (!n_rays)
+        return RTB200_OK;
+    const int S = (N - 1) * RTB_N_SUB, N2 = S + 1;
+    rc = upload_rays(ctx, rays, n_rays);
+    if (rc)
+        return rc;
+    rc = ensure_handoff(ctx, (long long) n_rays, true);
+    if (rc)
+        return rc;
+    RTB_CUDA(ctx->d_path_xy.reserve(n_rays * (size_t) N2));
+    RTB_CUDA(ctx->d_path_I.reserve(n_rays * (size_t) N2));
+    RTB_CUDA(ctx->d_err.reserve(n_rays));
+    RTB_CUDA(cudaMemsetAsync(ctx->d_path_xy.p, 0, n_rays * (size_t) N2 * sizeof(float2), ctx->stream));
+    RTB_CUDA(cudaMemsetAsync(ctx->d_path_I.p, 0, n_rays * (size_t) N2 * sizeof(float), ctx->stream));
+    Handoff h{ ctx->d_seg.p, ctx->d_meta.p, ctx->d_exit.p, ctx->d_path_xy.p };
+    Chunk ck;
+    std::memset(&ck, 0, sizeof(ck));
+    ck.ray1 = (long long) n_rays;
+    ck.rays = ctx->d_rays.p;
+    ck.tans = ctx->d_tans.p;
+    launch_march(ctx->prob, ck, true, h, ctx->d_fail, false, ctx->stream, ctx->d_work, true);
+    launch_path_intensity(ctx->prob, ck, h, ctx->d_path_I.p, ctx->d_err.p, ctx->stream);
+    ctx->launches += 2;
+    RTB_CUDA(cudaGetLastError());
+    std::vector<float2> xy(n_rays * (size_t) N2);
+    std::vector<int> err(n_rays);
+    RTB_CUDA(cudaMemcpyAsync(xy.data(), ctx->d_path_xy.p, xy.size() * sizeof(float2),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    if (Ir)
+        RTB_CUDA(cudaMemcpyAsync(Ir, ctx->d_path_I.p, n_rays * (size_t) N2 * sizeof(float),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    RTB_CUDA(cudaMemcpyAsync(err.data(), ctx->d_err.p, n_rays * sizeof(int), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    rc = finish(ctx, nullptr, nullptr, 0, nullptr);
+    if (rc < 0)
+        return rc;
+    int n_errors = 0;
+    for (size_t r = 0; r < n_rays; r++) {
+        for (int q = 0; q < N2; q++) {
+            if (xr)
+                xr[r * (size_t) N2 + q] = xy[r * (size_t) N2 + q].x;
+            if (yr)
+                yr[r * (size_t) N2 + q] = xy[r * (size_t) N2 + q].y;
+        }
+        if (error)
+            error[r] = err[r];
+        n_errors += err[r] != 0;
+    }
+    return n_errors ? RTB200_RAYS_FAILED : RTB200_OK;
 }
 
 int rtb200_measure_fp64_peak(rtb200_ctx *ctx, double *rate)

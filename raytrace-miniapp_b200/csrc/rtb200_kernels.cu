@@ -156,6 +156,7 @@ __device__ float atanf_fdlibm(float x)
 // ------------------------------------------------------------------------------------------
 struct GlobalSink {
     SegRec *seg;
+    float2 *path; // RAY_DEBUG trajectory of this ray (rtb200_calc_ray_paths) or null
     __device__ __forceinline__ void operator()(int idx, float gvl, float evl, int cell) const
     {
         int4 v;
@@ -164,6 +165,11 @@ struct GlobalSink {
         v.z = cell;
         v.w = 0;
         *reinterpret_cast<int4 *>(&seg[idx]) = v;
+    }
+    __device__ __forceinline__ void point(int idx, float x, float y) const
+    {
+        if (path)
+            path[idx] = make_float2(x, y);
     }
 };
 
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(128) march_kernel(const DevProblem P, const Ch
         ta = __ldg(&P.tanA[k]);
         tb = __ldg(&P.tanB[m]);
     }
-    GlobalSink sink{ h.seg + L * S };
+    GlobalSink sink{ h.seg + L * S, nullptr };
     MarchResult res;
     unsigned steps = 0;
     march_ray(P.planes, P.N, P.method, P.dz0, P.c, P.use_emis != 0, rx, ry, ta, tb, sink, res,
@@ -253,7 +259,7 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
     long long L = 0;
     float rx = 0.f, ry = 0.f, ra = 0.f, rb = 0.f;
     unsigned total_steps = 0;
-    GlobalSink sink{ h.seg };
+    GlobalSink sink{ h.seg, nullptr };
     for (;;) {
         const bool need = m.phase == PH_DONE && !dead;
         const unsigned want = __ballot_sync(0xffffffffu, need);
@@ -293,6 +299,11 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
                         h.meta[L] = RTB_META_INACTIVE;
                     } else {
                         sink.seg = h.seg + L * S;
+                        if (h.path) { // trajectory start point (:419-426)
+                            const int N2 = S + 1;
+                            sink.path = h.path + L * N2;
+                            sink.path[P.method == 1 ? S : 0] = make_float2(rx, ry);
+                        }
                         flat_init(m, P.planes, P.N, P.method, P.dz0, rx, ry, ta, tb);
                         if (m.phase == PH_DONE) // N == 1: nothing to march
                             h.meta[L] = 0u;
@@ -838,6 +849,7 @@ struct SmemSink {
         evl[idx * rb + slot] = e;
         cell[idx * rb + slot] = c;
     }
+    __device__ __forceinline__ void point(int, float, float) const {}
 };
 
 #define RTB_FUSED_WARPS 8
@@ -1358,6 +1370,109 @@ __global__ void __launch_bounds__(256)
     flush_pix();
     flush_bin();
     }
+}
+
+// Trajectory intensities of RayTrace::calc_ray_path (RAY_DEBUG path of RayTrace_calc_ray,
+// :536-566): one warp per explicit ray, lane = frequency bin, K <= 128.  With a debug buffer the
+// reference always integrates emission-style (:543), over ALL (segment, sub-segment) records in
+// order, and stores I = sum_k (float)(2*Iv[k]*dv[k]) after each one.
+__global__ void __launch_bounds__(256)
+    path_intensity_kernel(const DevProblem P, const Chunk c, const Handoff h, float *path_I, int *error)
+{
+    constexpr int KS = 4;
+    __shared__ double exp_tab[64];
+    load_exp_table(exp_tab);
+    const ArrayConsts KC{ P.kfp, exp_tab };
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long) gridDim.x * blockDim.x) >> 5;
+    const long long n = c.ray1 - c.ray0;
+    const int S = (P.N - 1) * RTB_N_SUB, N2 = S + 1, K = P.K;
+    for (long long slot = warp_id; slot < n; slot += n_warps) {
+        const unsigned meta = __ldg(&h.meta[slot]);
+        float *out = path_I + slot * N2;
+        if (meta & RTB_META_INVALID) { // error -1: returned before any intensity is computed
+            if (lane == 0)
+                error[slot] = -1;
+            continue;
+        }
+        const float4 r = __ldg(&c.rays[c.ray0 + slot]);
+        double f = 0.0;
+        if (P.seed_fv && !(meta & RTB_META_ESCAPED)) {
+            if (P.method == 1) {
+                const float4 e = h.exit_ray[slot];
+                f = dev_calc_seed(P, (double) e.x, (double) e.y, (double) e.z, (double) e.w);
+            } else {
+                f = dev_calc_seed(P, (double) r.x, (double) r.y, (double) r.z, (double) r.w);
+            }
+        }
+        double Iv[KS], dv[KS];
+        int koff[KS];
+#pragma unroll
+        for (int q = 0; q < KS; q++) {
+            const int k = lane + 32 * q;
+            koff[q] = min(k, K - 1);
+            dv[q] = k < K ? 0.5 * __ldg(&P.dv2[k]) : 0.0;
+            Iv[q] = (f != 0.0 && k < K) ? __dmul_rn(f, __ldg(&P.seed_fv[k])) : 0.0;
+        }
+        auto intensity = [&]() {
+            float part = 0.0f;
+#pragma unroll
+            for (int q = 0; q < KS; q++)
+                part += (float) (2 * Iv[q] * dv[q]);
+            for (int o = 16; o > 0; o >>= 1)
+                part += __shfl_xor_sync(0xffffffffu, part, o);
+            return part;
+        };
+        float I0 = intensity();
+        if (lane == 0)
+            out[0] = I0;
+        const int lo = meta & 0xfff, hi = (meta >> 12) & 0xfff;
+        const SegRec *seg = h.seg + slot * S;
+        for (int sg = 0; sg < S; sg++) {
+            if (sg >= lo && sg < hi) {
+                const int4 rv = __ldg(reinterpret_cast<const int4 *>(&seg[sg]));
+                const float gvl = __int_as_float(rv.x), evl = __int_as_float(rv.y);
+                if (!(gvl == 0.0f && evl == 0.0f)) {
+                    const float *row = P.planes[sg / RTB_N_SUB + 1].gv + (size_t) rv.z * K;
+#pragma unroll
+                    for (int q = 0; q < KS; q++) {
+                        const float g = __ldg(row + koff[q]);
+                        const float glf = __fmul_rn(gvl, g), elf = __fmul_rn(evl, g);
+                        const double gl = (double) glf, el = (double) elf;
+                        if (!(fabsf(glf) < 700.0f))
+                            Iv[q] = ase_update_library(Iv[q], gl, el);
+                        else if (fabsf(glf) < 1e-3f)
+                            Iv[q] = ase_update_small(Iv[q], gl, el, KC);
+                        else
+                            Iv[q] = ase_update_large(Iv[q], gl, el, rcp_approx(glf), KC);
+                    }
+                }
+            }
+            const float Is = intensity();
+            if (lane == 0)
+                out[sg + 1] = Is;
+        }
+        bool neg = false, nan = false;
+#pragma unroll
+        for (int q = 0; q < KS; q++) {
+            neg = neg || Iv[q] < 0.0;
+            nan = nan || Iv[q] != Iv[q];
+        }
+        const bool any_neg = __any_sync(0xffffffffu, neg), any_nan = __any_sync(0xffffffffu, nan);
+        if (lane == 0)
+            error[slot] = any_neg ? -2 : (any_nan ? -3 : 0);
+    }
+}
+
+void launch_path_intensity(const DevProblem &P, const Chunk &c, const Handoff &h, float *path_I,
+                           int *error, cudaStream_t st)
+{
+    const long long n = c.ray1 - c.ray0;
+    if (n <= 0)
+        return;
+    long long blocks = std::min<long long>((n + 7) / 8, 148LL * 8 * 4);
+    path_intensity_kernel<<<(unsigned) blocks, 256, 0, st>>>(P, c, h, path_I, error);
 }
 
 void launch_integrate_scatter(const DevProblem &P, const Chunk &c, bool list_mode,

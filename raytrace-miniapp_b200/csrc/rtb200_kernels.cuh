@@ -21,6 +21,7 @@ struct Handoff {
     SegRec *seg;        // [slots * S]
     unsigned *meta;     // [slots]
     float4 *exit_ray;   // [slots] ray2 = (x, y, a, b) at exit; may be null (ASE binning never reads it)
+    float2 *path;       // [slots * ((N-1)*3 + 1)] RAY_DEBUG trajectory (x, y); null except for calc_ray_paths
 };
 
 // Output selection of the integration kernel.
@@ -49,6 +50,8 @@ void launch_integrate_scatter(const DevProblem &P, const Chunk &c, bool list_mod
 // Returns false when the problem does not fit it; the caller falls back to the kernels above.
 bool launch_trace_ase_fused(const DevProblem &P, long long pix0, long long pix1, const Outputs &o,
                             cudaStream_t st);
+void launch_path_intensity(const DevProblem &P, const Chunk &c, const Handoff &h, float *path_I,
+                           int *error, cudaStream_t st);
 void launch_fp64_peak(double *out, int iters, cudaStream_t st, int *blocks, int *threads);
 
 } // namespace rtb

@@ -69,6 +69,9 @@ def load():
     L.rtb200_calc_rays.argtypes = [ctx, C.c_int, C.c_double, P(abi.GainPlane), P(abi.Seed),
                                    C.c_int, C.c_int, P(abi.Ray), C.c_size_t, C.c_void_p,
                                    P(abi.Ray), P(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p]
+    L.rtb200_calc_ray_paths.argtypes = [ctx, C.c_int, C.c_double, P(abi.GainPlane), P(abi.Seed),
+                                        C.c_int, abi.c_double_p, C.c_int, C.c_double, P(abi.Ray),
+                                        C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_int)]
     L.rtb200_stage.argtypes = [ctx, P(abi.CProblem), C.c_uint]
     L.rtb200_staged_pixels.argtypes = [ctx]
     L.rtb200_staged_pixels.restype = C.c_int64
@@ -190,6 +193,23 @@ class Context:
             ray2.ctypes.data_as(C.POINTER(abi.Ray)), err.ctypes.data_as(C.POINTER(C.c_int)),
             _addr(gvl), _addr(evl), _addr(ivl)))
         return dict(Iv=Iv, ray2=ray2, error=err, gvl=gvl, evl=evl, ivl=ivl)
+
+    def calc_ray_paths(self, problem, rays, method=None, c=0.5):
+        """RayTrace::calc_ray_path for a ray list: x, y, I [n_rays, 3*(N-1)+1] and error codes."""
+        rays = np.ascontiguousarray(rays, abi.ray_dtype)
+        n, N = rays.size, problem.N
+        method = problem.method if method is None else method
+        N2 = abi.N_SUB * (N - 1) + 1
+        planes = (abi.GainPlane * N)(*[g.c_struct() for g in problem.gain])
+        sd = problem.seed.c_struct() if problem.seed is not None else None
+        dv = np.ascontiguousarray(problem.euv_beam.dv, np.float64)
+        x, y, I = (np.zeros((n, N2), np.float32) for _ in range(3))
+        err = np.zeros(n, np.int32)
+        self._check(self.L.rtb200_calc_ray_paths(
+            self.h, N, problem.euv_beam.dz, planes, C.byref(sd) if sd else None, dv.size,
+            dv.ctypes.data_as(abi.c_double_p), method, c, rays.ctypes.data_as(C.POINTER(abi.Ray)), n,
+            _addr(x), _addr(y), _addr(I), err.ctypes.data_as(C.POINTER(C.c_int))))
+        return dict(x=x, y=y, I=I, error=err)
 
     # ---- device-resident calls -----------------------------------------------------------------
     def stage(self, problem, flags=0):

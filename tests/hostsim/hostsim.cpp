@@ -25,6 +25,7 @@ struct ArraySink {
         evl[idx] = e;
         ivl[idx] = cell;
     }
+    void point(int, float, float) const {}
 };
 } // namespace
 

@@ -203,3 +203,21 @@ def test_row_cyclic_shares_equal_whole_image(ase_small, ctx):
             acc_a += part_a
         assert torch.equal(acc_i, whole_i)
         assert rel_l2(acc_a.cpu().numpy(), whole_a.cpu().numpy()) < 1e-14
+
+
+def test_ray_trajectories(ase_small, seed_small, oracle, ctx):
+    """rtb200_calc_ray_paths == RayTrace::calc_ray_path (RAY_DEBUG trajectories): positions at the
+    sub-segment boundaries bit-exact, running intensity (a float sum over bins) to 1e-5."""
+    for (p, extra), c in ((ase_small, 0.5), (seed_small, 0.5), (ase_small, 0.3)):
+        rays = p.rays()[extra["sample_index"]][:400]
+        g = ctx.calc_ray_paths(p, rays, c=c)
+        o = oracle.calc_ray_paths(p, rays, c=c)
+        assert np.array_equal(g["error"], o["error"])
+        assert np.array_equal(g["x"].view(np.uint32), o["x"].view(np.uint32))
+        assert np.array_equal(g["y"].view(np.uint32), o["y"].view(np.uint32))
+        scale = np.abs(o["I"]).max(axis=1, keepdims=True) + 1e-30
+        assert np.max(np.abs(g["I"] - o["I"]) / scale) < 1e-5
+        assert o["I"].max() > 0
+        if c == 0.5:  # the committed trajectories of the unmodified reference
+            ref = extra["sample_debug"][:400].reshape(400, -1, 3)
+            assert np.array_equal(g["x"], ref[:, :, 0]) and np.array_equal(g["y"], ref[:, :, 1])
