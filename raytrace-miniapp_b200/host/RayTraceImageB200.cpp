@@ -66,6 +66,33 @@ rtb200_ctx *context()
     return tls.ctx;
 }
 
+// True when `rays` is the complete enumeration of the euv grid in create_image's order
+// (x slowest ... b fastest, coordinates rounded to float).  The size must match exactly; the
+// coordinates are checked on the first and last 64 rays and on 4096 evenly spaced ones.
+bool is_full_grid(const RayTrace::EUV_beam_struct &beam, const std::vector<ray_struct> &rays)
+{
+    const size_t Nt = (size_t) beam.nx * beam.ny * beam.na * beam.nb;
+    if (rays.size() != Nt || Nt == 0)
+        return false;
+    auto matches = [&](size_t ijkm) {
+        const int m = (int) (ijkm % beam.nb);
+        const int k = (int) ((ijkm / beam.nb) % beam.na);
+        const int j = (int) ((ijkm / ((size_t) beam.na * beam.nb)) % beam.ny);
+        const int i = (int) (ijkm / ((size_t) beam.ny * beam.na * beam.nb));
+        const ray_struct &r = rays[ijkm];
+        return r.x == (float) beam.x[i] && r.y == (float) beam.y[j] && r.a == (float) beam.a[k] &&
+               r.b == (float) beam.b[m];
+    };
+    for (size_t q = 0; q < 64 && q < Nt; q++)
+        if (!matches(q) || !matches(Nt - 1 - q))
+            return false;
+    const size_t step = Nt / 4096 + 1;
+    for (size_t q = 0; q < Nt; q += step)
+        if (!matches(q))
+            return false;
+    return true;
+}
+
 } // namespace
 
 // setID hook for RayTraceImageThreadLoop ("b200-multigpu").  The reference calls setID(i) in the
@@ -127,9 +154,33 @@ void RayTraceImageB200Loop(int N, const RayTrace::EUV_beam_struct &beam,
     rtb200_ctx *ctx = context();
     rtb200_ray failed[RTB200_N_FAILED_MAX];
     int n_failed = 0;
-    const int rc = rtb200_trace_rays(ctx, N, &b, planes.data(), seed ? &sd : nullptr, method,
-        reinterpret_cast<const rtb200_ray *>(rays.data()), rays.size(), scale, image, I_ang,
-        &failure_code, failed, RTB200_N_FAILED_MAX, &n_failed);
+    int rc;
+    if (method == 1 && !seed && scale == 1.0 && is_full_grid(beam, rays)) {
+        // create_image passed the complete ASE ray enumeration of the euv grid
+        // (src/RayTraceImage.cpp:300-328 with N_start = 0, N_parallel = 1): let the device
+        // enumerate the rays itself.  No ray upload, pixels owned by CTAs, no atomics on the image.
+        rtb200_problem prob;
+        memset(&prob, 0, sizeof(prob));
+        prob.N = N;
+        prob.N_start = 0;
+        prob.N_parallel = 1;
+        prob.euv_beam = &b;
+        prob.gain = planes.data();
+        const size_t n_img = (size_t) beam.nx * beam.ny * beam.nv, n_ang = (size_t) beam.na * beam.nb;
+        std::vector<double> tmp(n_img + n_ang);
+        rc = rtb200_create_image(ctx, &prob, RTB200_FLAG_NO_LIMITS, tmp.data(), tmp.data() + n_img,
+            &failure_code, failed, RTB200_N_FAILED_MAX, &n_failed);
+        if (rc >= 0) { // accumulate, like every *Loop (src/RayTraceImageCPU.cpp:56-68)
+            for (size_t i = 0; i < n_img; i++)
+                image[i] += tmp[i];
+            for (size_t i = 0; i < n_ang; i++)
+                I_ang[i] += tmp[n_img + i];
+        }
+    } else {
+        rc = rtb200_trace_rays(ctx, N, &b, planes.data(), seed ? &sd : nullptr, method,
+            reinterpret_cast<const rtb200_ray *>(rays.data()), rays.size(), scale, image, I_ang,
+            &failure_code, failed, RTB200_N_FAILED_MAX, &n_failed);
+    }
     if (rc < 0) {
         fprintf(stderr, "rtb200 error %d: %s\n", rc, rtb200_last_error(ctx));
         exit(-1);
