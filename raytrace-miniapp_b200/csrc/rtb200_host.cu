@@ -339,7 +339,7 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
         const size_t e0 = new_event(ctx, st);
         launch_march(P, c, false, h, ctx->d_fail, ctx->count_steps, st, ctx->d_work, ctx->flat_march);
         const size_t e1 = new_event(ctx, st);
-        if (ctx->owner_ok && !out.Iv && !out.error)
+        if (ctx->owner_ok && !out.Iv && !out.error && P.K <= 128) // one pass of <= 4 bin slots
             launch_integrate_ase_owner(P, c, h, out, st);
         else
             launch_integrate_scatter(P, c, false, h, out, st);
