@@ -163,6 +163,10 @@ def run_gpu(args):
     from raytrace_miniapp_b200 import build as rbuild, dist as rdist, lib as rl
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
         rbuild.build_library()  # no-op when librtb200.so is newer than its sources
+    else:  # the other ranks wait for local rank 0's (normally instantaneous) build
+        t_wait = time.time()
+        while rbuild.needs_build() and time.time() - t_wait < 300:
+            time.sleep(0.5)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
