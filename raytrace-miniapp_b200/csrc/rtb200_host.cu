@@ -121,6 +121,7 @@ struct rtb200_ctx {
     bool count_steps = false;
     bool use_fused = false; // opt-in (RTB200_FUSED=1): measured slower than the two-kernel path
     bool flat_march = true;
+    int march_blocks = 0; // grid of the persistent march on this device
     unsigned long long *d_work = nullptr;
     size_t handoff_bytes = (size_t) 4096 << 20; // B200 has 180 GB: one chunk for every shipped / synthetic size
 };
@@ -337,7 +338,7 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
         c.row_off = row_off;
         c.row_stride = row_stride;
         const size_t e0 = new_event(ctx, st);
-        launch_march(P, c, false, h, ctx->d_fail, ctx->count_steps, st, ctx->d_work, ctx->flat_march);
+        launch_march(P, c, false, h, ctx->d_fail, ctx->count_steps, st, ctx->d_work, ctx->flat_march, ctx->march_blocks);
         const size_t e1 = new_event(ctx, st);
         if (ctx->owner_ok && !out.Iv && !out.error && P.K <= 128) // one pass of <= 4 bin slots
             launch_integrate_ase_owner(P, c, h, out, st);
@@ -429,6 +430,7 @@ int rtb200_create(int device, rtb200_ctx **out)
     if ((e = cudaMalloc((void **) &ctx->d_work, sizeof(unsigned long long))) != cudaSuccess)
         return fail(e);
     std::memset(ctx->h_fail, 0, sizeof(FailState));
+    ctx->march_blocks = march_persistent_blocks();
     if (const char *s = getenv("RTB200_HANDOFF_MB"))
         ctx->handoff_bytes = (size_t) std::max(1, atoi(s)) << 20;
     if (const char *s = getenv("RTB200_COUNT_STEPS"))
@@ -683,7 +685,7 @@ int launch_list(rtb200_ctx *ctx, size_t n_rays, const Outputs &out_all, bool kee
         if (out.error)
             out.error += a;
         const size_t e0 = new_event(ctx, ctx->stream);
-        launch_march(P, c, true, h, ctx->d_fail, ctx->count_steps, ctx->stream, ctx->d_work, ctx->flat_march);
+        launch_march(P, c, true, h, ctx->d_fail, ctx->count_steps, ctx->stream, ctx->d_work, ctx->flat_march, ctx->march_blocks);
         const size_t e1 = new_event(ctx, ctx->stream);
         launch_integrate_scatter(P, c, true, h, out, ctx->stream);
         const size_t e2 = new_event(ctx, ctx->stream);
@@ -910,7 +912,7 @@ int rtb200_calc_ray_paths(rtb200_ctx *ctx, int N, double dz, const rtb200_gain_p
     ck.ray1 = (long long) n_rays;
     ck.rays = ctx->d_rays.p;
     ck.tans = ctx->d_tans.p;
-    launch_march(ctx->prob, ck, true, h, ctx->d_fail, false, ctx->stream, ctx->d_work, true);
+    launch_march(ctx->prob, ck, true, h, ctx->d_fail, false, ctx->stream, ctx->d_work, true, ctx->march_blocks);
     launch_path_intensity(ctx->prob, ck, h, ctx->d_path_I.p, ctx->d_err.p, ctx->stream);
     ctx->launches += 2;
     RTB_CUDA(cudaGetLastError());

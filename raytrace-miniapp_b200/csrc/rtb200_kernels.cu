@@ -154,9 +154,10 @@ __device__ float atanf_fdlibm(float x)
 // ------------------------------------------------------------------------------------------
 // march
 // ------------------------------------------------------------------------------------------
-struct GlobalSink {
+template <bool PATH>
+struct GlobalSinkT {
     SegRec *seg;
-    float2 *path; // RAY_DEBUG trajectory of this ray (rtb200_calc_ray_paths) or null
+    float2 *path; // RAY_DEBUG trajectory of this ray (rtb200_calc_ray_paths); unused unless PATH
     __device__ __forceinline__ void operator()(int idx, float gvl, float evl, int cell) const
     {
         int4 v;
@@ -168,10 +169,11 @@ struct GlobalSink {
     }
     __device__ __forceinline__ void point(int idx, float x, float y) const
     {
-        if (path)
+        if (PATH)
             path[idx] = make_float2(x, y);
     }
 };
+typedef GlobalSinkT<false> GlobalSink;
 
 template <bool LIST, bool COUNT>
 __global__ void __launch_bounds__(128) march_kernel(const DevProblem P, const Chunk c,
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(128) march_kernel(const DevProblem P, const Ch
 #ifndef RTB_MARCH_MINBLOCKS
 #define RTB_MARCH_MINBLOCKS 4
 #endif
-template <bool LIST, bool COUNT>
+template <bool LIST, bool COUNT, bool PATH = false>
 __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(const DevProblem P, const Chunk c,
                                                          const Handoff h, FailState *fail,
                                                          unsigned long long *work)
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
     long long L = 0;
     float rx = 0.f, ry = 0.f, ra = 0.f, rb = 0.f;
     unsigned total_steps = 0;
-    GlobalSink sink{ h.seg, nullptr };
+    GlobalSinkT<PATH> sink{ h.seg, nullptr };
     for (;;) {
         const bool need = m.phase == PH_DONE && !dead;
         const unsigned want = __ballot_sync(0xffffffffu, need);
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
                         h.meta[L] = RTB_META_INACTIVE;
                     } else {
                         sink.seg = h.seg + L * S;
-                        if (h.path) { // trajectory start point (:419-426)
+                        if (PATH) { // trajectory start point (:419-426)
                             const int N2 = S + 1;
                             sink.path = h.path + L * N2;
                             sink.path[P.method == 1 ? S : 0] = make_float2(rx, ry);
@@ -353,27 +355,19 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
 
 void launch_march(const DevProblem &P, const Chunk &c, bool list_mode, const Handoff &h,
                   FailState *fail, bool count_steps, cudaStream_t st, unsigned long long *work,
-                  bool flat)
+                  bool flat, int persistent_blocks)
 {
     const long long n = list_mode ? (c.ray1 - c.ray0) : (c.pix1 - c.pix0) * P.ab_max;
     if (n <= 0)
         return;
     const int threads = 128;
     if (flat) {
-        static int per_sm = 0, sms = 0;
-        if (per_sm == 0) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, march_flat_kernel<false, false>,
-                                                          threads, 0);
-            if (per_sm < 1)
-                per_sm = 1;
-        }
-        long long blocks = (long long) sms * per_sm;
+        long long blocks = persistent_blocks > 0 ? persistent_blocks : 148 * 4;
         blocks = std::min(blocks, (n + threads - 1) / threads);
         cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
-        if (list_mode) {
+        if (list_mode && h.path) { // trajectories (rtb200_calc_ray_paths)
+            march_flat_kernel<true, false, true><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, fail, work);
+        } else if (list_mode) {
             if (count_steps)
                 march_flat_kernel<true, true><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, fail, work);
             else
@@ -728,7 +722,7 @@ __device__ __forceinline__ int integrate_ray_gain_fast(const DevProblem &P, cons
 
 #define RTB_OWNER_WARPS 8
 #ifndef RTB_OWNER_MINBLOCKS
-#define RTB_OWNER_MINBLOCKS 3
+#define RTB_OWNER_MINBLOCKS 4
 #endif
 
 template <int KS>
@@ -1525,6 +1519,16 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters)
     const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
     if (r == 12345.678)
         out[0] = r; // never true; keeps the chains alive
+}
+
+// Grid of the persistent march: resident CTAs per SM (occupancy) x SMs of the current device.
+int march_persistent_blocks()
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, march_flat_kernel<false, false>, 128, 0);
+    return std::max(1, per_sm) * std::max(1, sms);
 }
 
 void launch_fp64_peak(double *out, int iters, cudaStream_t st, int *blocks, int *threads)

@@ -37,7 +37,8 @@ struct Outputs {
 // the launcher); flat = false: the literal nested form, one thread per ray.
 void launch_march(const DevProblem &P, const Chunk &c, bool list_mode, const Handoff &h,
                   FailState *fail, bool count_steps, cudaStream_t st, unsigned long long *work,
-                  bool flat);
+                  bool flat, int persistent_blocks);
+int march_persistent_blocks(); // for the current device; cached per context by the host layer
 // ASE (method 1, emission + gain), grid mode: one CTA per source pixel, the pixel's spectrum is
 // owned by the CTA (plain stores), I_ang by atomics.
 void launch_integrate_ase_owner(const DevProblem &P, const Chunk &c, const Handoff &h,

@@ -221,3 +221,24 @@ def test_ray_trajectories(ase_small, seed_small, oracle, ctx):
         if c == 0.5:  # the committed trajectories of the unmodified reference
             ref = extra["sample_debug"][:400].reshape(400, -1, 3)
             assert np.array_equal(g["x"], ref[:, :, 0]) and np.array_equal(g["y"], ref[:, :, 1])
+
+
+@pytest.mark.parametrize("env", [{"RTB200_FLAT_MARCH": "0"}, {"RTB200_FUSED": "1"}, {"RTB200_HANDOFF_MB": "8"}],
+                         ids=["nested-march", "fused-kernel", "small-handoff-chunks"])
+def test_alternative_kernel_paths(env, ase_small, rtlib, monkeypatch):
+    """The literal nested march kernel, the opt-in fused kernel and a hand-off arena that forces
+    many chunks give the same image as the default path (bit for bit: same march, same per-pixel
+    summation order)."""
+    p, extra = ase_small
+    base = rtlib.Context(0)
+    img0, ang0 = base.create_image(p)
+    base.close()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    alt = rtlib.Context(0)
+    img1, ang1 = alt.create_image(p)
+    alt.close()
+    check_image((img1, ang1), (extra["ref_cpu_image"], extra["ref_cpu_I_ang"]))
+    if "RTB200_FUSED" not in env:  # the fused kernel sums a pixel's rays in another order
+        assert np.array_equal(img0, img1)
+    assert rel_l2(img1, img0) < 1e-14
