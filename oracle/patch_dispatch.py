@@ -32,6 +32,7 @@ extern void RayTraceImageB200Loop( int N, const RayTrace::EUV_beam_struct& euv_b
     double scale, double *image, double *I_ang, unsigned int &failure_code,
     std::vector<ray_struct> &failed_rays );
 extern void RayTraceImageB200SetDevice( int device );
+extern void RayTraceImageB200Direct( const RayTrace::create_image_struct *info, double *image, double *I_ang );
 extern "C" int rtb200_device_count( void );
 '''
 anchor = "/**********************************************************************\n* Call RayTraceImage function from a thread loop"
@@ -45,6 +46,21 @@ branch = '''    } else if ( compute_method == "b200" ) {
             N, std::ref(*info->euv_beam), info->gain, info->seed,
             method, rays, scale, image, I_ang, failure_code, failed_rays );
 '''
+# full-speed entry, before the host ray list is built (:277)
+direct = '''    {
+        std::string m2 = compute_method;
+        std::transform( m2.begin(), m2.end(), m2.begin(), ::tolower );
+        if ( m2 == "b200-direct" ) {
+            RayTraceImageB200Direct( info, image, I_ang );
+            PROFILE_STOP( "create_image" );
+            return;
+        }
+    }
+
+'''
+anchor3 = "    // Create a list of rays to propagate\n"
+assert s.count(anchor3) == 1
+s = s.replace(anchor3, direct + anchor3)
 anchor2 = '    } else if ( compute_method == "cpu" ) {'
 assert s.count(anchor2) == 1
 s = s.replace(anchor2, branch + anchor2)

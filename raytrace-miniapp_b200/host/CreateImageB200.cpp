@@ -88,14 +88,16 @@ int main(int argc, char *argv[])
         const size_t n_ang = (size_t) info->euv_beam->na * info->euv_beam->nb;
         // warm-up of the GPU back-end (the reference does the same for its Cuda methods,
         // src/CreateImage.cpp:118-132)
-        for (size_t m = 0; m < methods.size(); m++)
-            if (methods[m].substr(0, 4) == "b200") {
+        for (size_t m = 0; m < methods.size(); m++) {
+            std::string lower = methods[m];
+            std::transform(lower.begin(), lower.end(), lower.begin(), ::tolower);
+            if (lower.substr(0, 4) == "b200" || lower.substr(0, 4) == "cuda") {
                 RayTrace::create_image(info, methods[m]);
                 free(info->image);
                 free(info->I_ang);
                 info->image = info->I_ang = NULL;
-                break;
             }
+        }
         std::vector<double> cpu_image, cpu_ang;
         std::vector<std::vector<double> > time(methods.size());
         for (size_t m = 0; m < methods.size(); m++) {
