@@ -23,11 +23,16 @@ REF_SO = os.path.join(_HERE, "_ref", "libref_oracle.so")
 REF_ROOT = "/root/reference"
 
 
-def build(ref=True, quiet=True):
-    """Compile the C restatement, and the reference library when /root/reference is present."""
+def build(ref=True, quiet=True, integration=False):
+    """Compile the C restatement, and the reference library when /root/reference is present.
+    integration=True also links the reference's driver with the B200 back-end registered
+    (CreateImage_b200, CreateImageB200) and the legacy-CUDA comparison binary; these need
+    raytrace-miniapp_b200/librtb200.so to exist."""
     targets = ["oracle"]
     if ref and os.path.isdir(os.path.join(REF_ROOT, "src")):
         targets.append("ref")
+        if integration:
+            targets += ["b200", "legacy"]
     out = subprocess.run(["make", "-C", _HERE, "-j8"] + targets, capture_output=quiet, text=True)
     if out.returncode != 0:
         raise RuntimeError("oracle build failed:\n%s\n%s" % (out.stdout, out.stderr))

@@ -95,6 +95,19 @@ def device_count():
     return load().rtb200_device_count()
 
 
+def _check_out(a, n, name):
+    """An output buffer handed to the C ABI must be n contiguous float64 values."""
+    if a is None or isinstance(a, int):
+        return
+    if hasattr(a, "data_ptr"):  # torch tensor
+        import torch
+        ok = a.dtype == torch.float64 and a.is_contiguous() and a.numel() == n
+    else:
+        ok = a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.size == n
+    if not ok:
+        raise ValueError("%s must be a contiguous float64 buffer of %d elements" % (name, n))
+
+
 def _addr(a):
     """Host numpy array / torch tensor (host or device) / int -> raw address."""
     if a is None:
@@ -142,6 +155,8 @@ class Context:
         cp, keep = problem.c_struct()
         image = np.empty(e.nx * e.ny * e.nv) if image is None else image
         I_ang = np.empty(e.na * e.nb) if I_ang is None else I_ang
+        _check_out(image, e.nx * e.ny * e.nv, "image")
+        _check_out(I_ang, e.na * e.nb, "I_ang")
         fc, nf = C.c_uint(0), C.c_int(0)
         failed = np.zeros(abi.N_FAILED_MAX, abi.ray_dtype)
         rc = self._check(self.L.rtb200_create_image(
@@ -162,6 +177,8 @@ class Context:
         rays = np.ascontiguousarray(rays, abi.ray_dtype)
         image = np.zeros(e.nx * e.ny * e.nv) if image is None else image
         I_ang = np.zeros(e.na * e.nb) if I_ang is None else I_ang
+        _check_out(image, e.nx * e.ny * e.nv, "image")
+        _check_out(I_ang, e.na * e.nb, "I_ang")
         fc, nf = C.c_uint(0), C.c_int(0)
         failed = np.zeros(abi.N_FAILED_MAX, abi.ray_dtype)
         self._check(self.L.rtb200_trace_rays(
