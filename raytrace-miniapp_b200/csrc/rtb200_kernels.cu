@@ -1078,7 +1078,7 @@ __device__ __forceinline__ int dev_get_index(int n, const double *x, double dx, 
         return 0;
     if (Y > xn)
         return n;
-    int k = (int) ceil((Y - x0) / dx); // guess
+    int k = (int) ceil((Y - x0) * (1.0 / dx)); // guess (1/dx: dx is warp-uniform per grid)
     k = k < 0 ? 0 : (k > n - 1 ? n - 1 : k);
     while (k > 0 && __ldg(&x[k - 1]) >= Y)
         --k;
@@ -1235,11 +1235,12 @@ __global__ void __launch_bounds__(256)
                 }
             }
         } else {
-            const long long p = phys_pixel(P, c, c.pix0 + slot / P.ab_max);
-            const int t = (int) (slot % P.ab_max);
+            const unsigned lq = (unsigned) slot / (unsigned) P.ab_max; // slots fit 32 bits
+            const long long p = phys_pixel(P, c, c.pix0 + lq);
+            const int t = (int) ((unsigned) slot - lq * (unsigned) P.ab_max);
             const PixelRays pr = pixel_rays(P, p);
             const int ab = pr.ab0 + t * (int) P.n_parallel;
-            const int ka = ab / P.snb, m = ab % P.snb;
+            const int ka = (int) ((unsigned) ab / (unsigned) P.snb), m = ab - ka * P.snb;
             rx = __ldg(&P.sxf[pr.i]);
             ry = __ldg(&P.syf[pr.j]);
             ra = __ldg(&P.saf[ka]);
@@ -1269,10 +1270,18 @@ __global__ void __launch_bounds__(256)
                 if (by < 0.0f && P.y_mirror)
                     by = -by;
             }
-            i1 = dev_get_index(P.nx, P.ex, P.edx, (double) bx);
-            i2 = dev_get_index(P.ny, P.ey, P.edy, (double) by);
-            i3 = dev_get_index(P.na, P.ea, P.eda, (double) ba);
-            i4 = dev_get_index(P.nb, P.eb, P.edb, (double) bb);
+            // the four destination indices are independent: lanes 0..3 search one grid each
+            // (x, y, a, b) and the results are broadcast, instead of 32 lanes repeating all four
+            const int d = lane & 3;
+            const int nn = d == 0 ? P.nx : (d == 1 ? P.ny : (d == 2 ? P.na : P.nb));
+            const double *xx = d == 0 ? P.ex : (d == 1 ? P.ey : (d == 2 ? P.ea : P.eb));
+            const double dd = d == 0 ? P.edx : (d == 1 ? P.edy : (d == 2 ? P.eda : P.edb));
+            const float yy = d == 0 ? bx : (d == 1 ? by : (d == 2 ? ba : bb));
+            const int idx = dev_get_index(nn, xx, dd, (double) yy);
+            i1 = __shfl_sync(0xffffffffu, idx, 0);
+            i2 = __shfl_sync(0xffffffffu, idx, 1);
+            i3 = __shfl_sync(0xffffffffu, idx, 2);
+            i4 = __shfl_sync(0xffffffffu, idx, 3);
         }
         double w = 0.0;
         bool bad = false;
