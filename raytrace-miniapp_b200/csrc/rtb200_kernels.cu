@@ -674,13 +674,16 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
 
 // Gain-only ray integrator of the seeded path (RayTraceImageHelper.h:569-581):
 //     Iv[k] *= exp( sum over records of (double) gvl * (double) gv[cell][k] ).
-// Records are fetched with one coalesced load per 32 and handed out by shuffles; all lineshape
-// row loads of a ray are independent, so they are in flight together.
+// Lane j fetches record c0 + j (one coalesced 16-byte load), widens gvl and resolves the address
+// of its lineshape row, and parks both in the warp's shared-memory slab; the warp then walks
+// the slab with one 16-byte broadcast read per record.  The product of two floats is exact in
+// double (48 significant bits, no underflow), so RN(gl + RN(gvl*gv)) == fma(gvl, gv, gl): one
+// DFMA per bin and record, bit-identical to the reference's multiply-then-add.
 template <int KS>
 __device__ __forceinline__ int integrate_ray_gain_fast(const DevProblem &P, const float *const *s_gv,
                                                        const SegRec *seg, unsigned meta, int lane,
                                                        int kbase, double (&Iv)[KS],
-                                                       const ArrayConsts &KC)
+                                                       const ArrayConsts &KC, unsigned slab)
 {
     const int lo = meta & 0xfff, hi = (meta >> 12) & 0xfff;
     const int K = P.K;
@@ -693,19 +696,30 @@ __device__ __forceinline__ int integrate_ray_gain_fast(const DevProblem &P, cons
     }
     for (int c0 = lo; c0 < hi; c0 += 32) {
         const int cnt = min(32, hi - c0);
-        int4 rv = make_int4(0, 0, 0, 0);
-        if (lane < cnt)
-            rv = __ldg(reinterpret_cast<const int4 *>(&seg[c0 + lane]));
+        __syncwarp();
+        if (lane < cnt) {
+            const int4 rv = __ldg(reinterpret_cast<const int4 *>(&seg[c0 + lane]));
+            const float *row = s_gv[(c0 + lane) / RTB_N_SUB + 1] + (size_t) rv.z * K;
+            const unsigned long long ra = reinterpret_cast<unsigned long long>(row);
+            const unsigned long long gd =
+                (unsigned long long) __double_as_longlong((double) __int_as_float(rv.x));
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slab + 16u * (unsigned) lane),
+                         "r"((unsigned) gd), "r"((unsigned) (gd >> 32)), "r"((unsigned) ra),
+                         "r"((unsigned) (ra >> 32))
+                         : "memory");
+        }
+        __syncwarp();
         for (int j = 0; j < cnt; j++) {
-            const float gvlf = __int_as_float(__shfl_sync(0xffffffffu, rv.x, j));
-            const int cell = __shfl_sync(0xffffffffu, rv.z, j);
-            if (gvlf == 0.0f)
-                continue; // adds exactly +0 to every bin
-            const double gvl = (double) gvlf;
-            const float *row = s_gv[(c0 + j) / RTB_N_SUB + 1] + (size_t) cell * K;
+            uint4 e;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
+                         : "r"(slab + 16u * (unsigned) j));
+            // a record with gvl == 0 adds exactly +0 to every bin: fma(0, gv, gl) == gl
+            const double gvl = __longlong_as_double((long long) (((unsigned long long) e.y << 32) | e.x));
+            const float *row = reinterpret_cast<const float *>(((unsigned long long) e.w << 32) | e.z);
 #pragma unroll
             for (int q = 0; q < KS; q++)
-                gl[q] = __dadd_rn(gl[q], __dmul_rn(gvl, (double) __ldg(row + koff[q])));
+                gl[q] = __fma_rn(gvl, (double) __ldg(row + koff[q]), gl[q]);
         }
     }
     bool neg = false, nan = false;
@@ -1169,6 +1183,7 @@ __global__ void __launch_bounds__(256)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double exp_tab[64];
+    __shared__ uint4 rec_slab[8][32]; // per-warp record + row-address slab (256 threads)
     const float **s_gv = reinterpret_cast<const float **>(smem_raw); // [N] gv base pointers
     for (int i = threadIdx.x; i < P.N; i += blockDim.x)
         s_gv[i] = P.planes[i].gv;
@@ -1176,6 +1191,8 @@ __global__ void __launch_bounds__(256)
     const ArrayConsts KC{ P.kfp, exp_tab };
     const bool gain_only = P.use_emis == 0;
     const int lane = threadIdx.x & 31;
+    const unsigned slab =
+        __shfl_sync(0xffffffffu, (unsigned) __cvta_generic_to_shared(&rec_slab[threadIdx.x >> 5][0]), 0);
     const long long warp_id = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long) gridDim.x * blockDim.x) >> 5;
     const long long n_slots = LIST ? (c.ray1 - c.ray0) : (c.pix1 - c.pix0) * P.ab_max;
@@ -1294,7 +1311,7 @@ __global__ void __launch_bounds__(256)
             }
             if (!invalid) {
                 const int cc = gain_only
-                                   ? integrate_ray_gain_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, kbase, Iv, KC)
+                                   ? integrate_ray_gain_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, kbase, Iv, KC, slab)
                                    : integrate_ray<KS>(P, h.seg + slot * S, meta, lane, kbase, Iv, exp_tab);
                 if (cc != 0) {
                     code = code == 0 ? cc : (cc < code ? cc : code); // negative (2) wins over NaN (3)
@@ -1339,7 +1356,7 @@ __global__ void __launch_bounds__(256)
                     Iv[q] = (f != 0.0 && k < K) ? __dmul_rn(f, __ldg(&P.seed_fv[k])) : 0.0;
                 }
                 if (gain_only)
-                    integrate_ray_gain_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, kbase, Iv, KC);
+                    integrate_ray_gain_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, kbase, Iv, KC, slab);
                 else
                     integrate_ray<KS>(P, h.seg + slot * S, meta, lane, kbase, Iv, exp_tab);
 #pragma unroll
