@@ -245,6 +245,12 @@ __global__ void __launch_bounds__(128) march_kernel(const DevProblem P, const Ch
 #ifndef RTB_MARCH_MINBLOCKS
 #define RTB_MARCH_MINBLOCKS 4
 #endif
+#ifndef RTB_MARCH_CHUNK
+#define RTB_MARCH_CHUNK 32
+#endif
+#ifndef RTB_REFILL_MIN
+#define RTB_REFILL_MIN 6
+#endif
 template <bool LIST, bool COUNT, bool PATH = false>
 __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(const DevProblem P, const Chunk c,
                                                          const Handoff h, FailState *fail,
@@ -257,25 +263,41 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
     FlatMarch m;
     m.phase = PH_DONE;
     m.steps = 0;
-    bool dead = false;
-    long long L = 0;
+    bool dead = false, exhausted = false;
+    long long L = 0, run_next = 0, run_end = 0;
     float rx = 0.f, ry = 0.f, ra = 0.f, rb = 0.f;
     unsigned total_steps = 0;
     GlobalSinkT<PATH> sink{ h.seg, nullptr };
     for (;;) {
         const bool need = m.phase == PH_DONE && !dead;
         const unsigned want = __ballot_sync(0xffffffffu, need);
-        if (want != 0u) {
-            const int leader = __ffs(want) - 1;
-            unsigned long long first = 0;
-            if (lane == leader)
-                first = atomicAdd(work, (unsigned long long) __popc(want));
-            first = __shfl_sync(0xffffffffu, first, leader);
+        // Refills run for at least RTB_REFILL_MIN lanes at a time (or when the warp has nothing
+        // else to do): the ~200 instructions of a ray start are issued for the whole warp.
+        if (want != 0u && (RTB_REFILL_MIN <= 1 || __popc(want) >= RTB_REFILL_MIN ||
+                           __ballot_sync(0xffffffffu, m.phase != PH_DONE) == 0u)) {
+            // The warp owns a run of RTB_MARCH_CHUNK consecutive slots and hands them to its
+            // lanes; one atomic per run instead of one per refill, and the rays a warp marches
+            // together are neighbours (same source pixel, adjacent angles), so they cross the
+            // same cells at about the same time.
+            if (run_next >= run_end && !exhausted) { // warp-uniform
+                unsigned long long first = 0;
+                if (lane == 0)
+                    first = atomicAdd(work, (unsigned long long) RTB_MARCH_CHUNK);
+                first = __shfl_sync(0xffffffffu, first, 0);
+                run_next = (long long) first;
+                run_end = run_next + RTB_MARCH_CHUNK < n_slots ? run_next + RTB_MARCH_CHUNK : n_slots;
+                if (run_next >= n_slots) {
+                    exhausted = true;
+                    run_end = run_next;
+                }
+            }
+            const long long mine = run_next + __popc(want & ((1u << lane) - 1u));
+            const long long after = run_next + __popc(want);
             if (need) {
-                L = (long long) first + __popc(want & ((1u << lane) - 1u));
-                if (L >= n_slots) {
-                    dead = true;
+                if (mine >= run_end) {
+                    dead = exhausted; // otherwise: served from the next run on the next trip
                 } else {
+                    L = mine;
                     float ta, tb;
                     bool active = true;
                     if (LIST) {
@@ -312,6 +334,7 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
                     }
                 }
             }
+            run_next = after < run_end ? after : run_end;
         }
         if (__ballot_sync(0xffffffffu, m.phase != PH_DONE) == 0u) {
             if (__ballot_sync(0xffffffffu, !dead) == 0u)

@@ -90,6 +90,63 @@ inline double host_interp_pchip(size_t N, const double *xi, const double *yi, do
     return f1 + t2 * (2 * t - 3) * (f1 - f2) + t * g1 - t2 * (g1 + (1 - t) * (g1 + g2));
 }
 
+// Is ddiv_by(a, b, RN(1/b)) == RN(a / b) for EVERY a?  (rtb200_math.cuh)
+//
+// With y = RN(1/b), q0 = RN(a*y), r = a - b*q0 and q1 = RN(q0 + r*y), the value rounded last is
+// a/b + (a/b - q0)*(b*y - 1): it misses a/b by less than 2^-104 relative (|a/b - q0| <= 2 ulp,
+// |b*y - 1| < 2^-53, plus the rounding of r should it be inexact), so q1 can only differ from
+// RN(a/b) when a/b lies that close to a midpoint of two doubles.  Scale a and b to integer
+// significands A, B in [2^52, 2^53): a midpoint is M*2^-53 (A >= B) or M*2^-54 (A < B) with M odd
+// in (2^53, 2^54), and |A/B - midpoint| = |D| / (B*2^s), D = A*2^s - B*M a non-zero integer, s = 53
+// or 54.  Closeness therefore needs |D| < 8 (|D| <= 16 is searched), and for a given B every such A follows from the
+// congruence B*M = -D (mod 2^s).  The handful of candidates is enumerated and the algorithm is
+// run on each; a divisor that fails once is not used with ddiv_by (the plane falls back to IEEE
+// divisions).  `witness` (optional) receives a failing numerator.  Floating point is scale
+// invariant, so the verdict holds for every binade of a and b short of over/underflow.
+// `rb_test` (tests only) replaces RN(1/B) for the integer-scaled divisor B: a reciprocal that is
+// one ulp off must be rejected, which is how tests/test_math_identities.py checks the search.
+inline bool markstein_safe(double b, double *witness = nullptr, double rb_test = 0.0)
+{
+    if (!(b > 0.0) || !std::isnormal(b))
+        return false;
+    int eb;
+    const double mb = std::frexp(b, &eb); // [0.5, 1)
+    const uint64_t B = (uint64_t) std::ldexp(mb, 53);
+    const double bd = (double) B, rb = rb_test != 0.0 ? rb_test : 1.0 / bd;
+    int t = 0;
+    while (((B >> t) & 1u) == 0u)
+        t++;
+    const uint64_t Bodd = B >> t;
+    uint64_t inv = Bodd; // inverse of Bodd modulo 2^64 (Newton; 3 correct bits to start with)
+    for (int it = 0; it < 6; it++)
+        inv *= 2u - Bodd * inv;
+    const uint64_t two52 = 1ull << 52, two53 = 1ull << 53, two54 = 1ull << 54;
+    for (int s = 53; s <= 54; s++) {
+        for (int D = -16; D <= 16; D++) {
+            if (D == 0 || t > 4 || (D % (1 << t)) != 0)
+                continue; // B*M + D must be divisible by 2^s, hence D by 2^t
+            const int bits = s - t; // modulus of the congruence for M
+            const uint64_t mask = (1ull << bits) - 1u;
+            const uint64_t rhs = (uint64_t) (int64_t) (-D / (1 << t));
+            for (uint64_t M = (rhs * inv) & mask; M < two54; M += mask + 1u) {
+                if (M <= two53 || (M & 1u) == 0u)
+                    continue;
+                const unsigned __int128 num = (unsigned __int128) B * M + (__int128) D;
+                const uint64_t A = (uint64_t) (num >> s);
+                if (A < two52 || A >= two53 || ((unsigned __int128) A << s) != num)
+                    continue;
+                const double a = (double) A;
+                if (ddiv_by(a, bd, rb) != a / bd) {
+                    if (witness)
+                        *witness = rb_test != 0.0 ? a : std::ldexp(a, eb - 53); // same significands
+                    return false;
+                }
+            }
+        }
+    }
+    return true;
+}
+
 // Interval table of one axis (AxisCell, rtb200_march.cuh): entry k describes [c[k-1], c[k]].
 inline void fill_axis_cells(const double *c, int n, AxisCell *t)
 {
@@ -182,6 +239,8 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
                     rw[k] = 1.0 / w;
                     rd[k] = 1.0 / (double) (float) w;
                     ok = ok && std::isnormal(rw[k]) && std::isnormal(rd[k]) && std::isnormal(w);
+                    // every numerator must divide exactly through the tabulated reciprocal
+                    ok = ok && markstein_safe(w) && markstein_safe((double) (float) w);
                 }
             };
             recip(g.x, g.Nx, rwx, rdx);

@@ -182,6 +182,33 @@ long long hostsim_check_ddiv_by(long long n, unsigned long long seed)
     }
     return bad;
 }
+// markstein_safe (rtb200_pack.h): the per-divisor proof obligation of ddiv_by.
+int hostsim_markstein_safe(double b, double *witness, double rb_test)
+{
+    return markstein_safe(b, witness, rb_test) ? 1 : 0;
+}
+double hostsim_ddiv_by(double a, double b) { return ddiv_by(a, b, 1.0 / b); }
+double hostsim_ddiv_by_rb(double a, double b, double rb) { return ddiv_by(a, b, rb); }
+// Searches random divisors in [2^-20, 2^-19) for one that markstein_safe rejects; returns the
+// number of rejected divisors among `n` and the last one with its witness numerator.
+long long hostsim_find_unsafe_divisor(long long n, unsigned long long seed, double *b_out, double *a_out)
+{
+    unsigned long long st = seed * 2862933555777941757ULL + 3037000493ULL;
+    long long found = 0;
+    for (long long i = 0; i < n; i++) {
+        st ^= st << 13;
+        st ^= st >> 7;
+        st ^= st << 17;
+        const double b = ldexp(1.0 + (double) (st >> 12) / 4503599627370496.0, -20);
+        double w = 0.0;
+        if (!markstein_safe(b, &w)) {
+            found++;
+            *b_out = b;
+            *a_out = w;
+        }
+    }
+    return found;
+}
 // Every float in [lo_bits, hi_bits] (bit patterns, both signs) for fdiv_const with c.
 long long hostsim_check_fdiv_const(float c, unsigned lo_bits, unsigned hi_bits)
 {
