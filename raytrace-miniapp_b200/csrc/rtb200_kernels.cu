@@ -675,12 +675,18 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
 #pragma unroll
             for (int q = 0; q < KS; q++) {
                 const double gl = (double) glf[q], el = (double) elf[q];
-                double a = 0.0, b = 0.0;
-                if (flags & (1u << (2 * q))) // warp-uniform
-                    a = ase_update_small(Iv[q], gl, el, KC);
-                if (flags & (2u << (2 * q))) // warp-uniform
-                    b = ase_update_large(Iv[q], gl, el, rcp_approx(glf[q]), KC);
-                Iv[q] = small[q] ? a : b;
+                const unsigned f = (flags >> (2 * q)) & 3u; // warp-uniform
+                // three straight-line variants: the common one (every lane of the slot on the
+                // exp branch) carries no select and no dead Taylor result
+                if (f == 2u) {
+                    Iv[q] = ase_update_large(Iv[q], gl, el, rcp_approx(glf[q]), KC);
+                } else if (f == 1u) {
+                    Iv[q] = ase_update_small(Iv[q], gl, el, KC);
+                } else {
+                    const double a = ase_update_small(Iv[q], gl, el, KC);
+                    const double b = ase_update_large(Iv[q], gl, el, rcp_approx(glf[q]), KC);
+                    Iv[q] = small[q] ? a : b;
+                }
             }
         }
     }
