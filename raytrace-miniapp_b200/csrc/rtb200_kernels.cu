@@ -627,35 +627,17 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
                          : "memory");
         }
         __syncwarp();
-        uint4 e = slab_load(0);
-        float gn[KS];
-        {
-            const float *row = reinterpret_cast<const float *>(((unsigned long long) e.w << 32) | e.z);
-#pragma unroll
-            for (int q = 0; q < KS; q++)
-                gn[q] = __ldg(row + koff[q]);
-        }
-        for (int j = 0; j < cnt; j++) {
-            const float gvl = __uint_as_float(e.x), evl = __uint_as_float(e.y);
-            float g[KS];
-#pragma unroll
-            for (int q = 0; q < KS; q++)
-                g[q] = gn[q];
-            if (j + 1 < cnt) { // request the next record's row before integrating this one
-                e = slab_load(j + 1);
-                const float *row = reinterpret_cast<const float *>(((unsigned long long) e.w << 32) | e.z);
-#pragma unroll
-                for (int q = 0; q < KS; q++)
-                    gn[q] = __ldg(row + koff[q]);
-            }
+        // The update of one record; `g` are the lineshape values of this lane's bins.
+        auto update = [&](float gvl, float evl, const float (&g)[KS]) {
             if (gvl == 0.0f && evl == 0.0f)
-                continue; // gl = el = 0: the update is the identity
+                return; // gl = el = 0: the update is the identity
             // One warp-wide OR gathers every branch decision of the record: bit 2q = "some lane
             // of slot q takes the Taylor branch", bit 2q+1 = "some lane takes the exp branch",
             // bit 31 = "some |gl| >= 700, inf or NaN" (library semantics).
             float glf[KS], elf[KS];
             bool small[KS];
             unsigned flags = 0u;
+            float ag_sum = 0.0f; // one range test for all slots: sum of |gl| (NaN and inf propagate)
 #pragma unroll
             for (int q = 0; q < KS; q++) {
                 glf[q] = __fmul_rn(gvl, g[q]);
@@ -663,14 +645,15 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
                 const float ag = fabsf(glf[q]);
                 small[q] = ag < 1e-3f; // == (fabs((double) glf) < 1e-3)
                 flags |= (small[q] ? 1u : 2u) << (2 * q);
-                flags |= !(ag < 700.0f) ? 0x80000000u : 0u;
+                ag_sum += ag;
             }
+            flags |= !(ag_sum < 700.0f) ? 0x80000000u : 0u; // conservative: library path is always valid
             flags = __reduce_or_sync(0xffffffffu, flags);
             if (flags & 0x80000000u) {
 #pragma unroll
                 for (int q = 0; q < KS; q++)
                     Iv[q] = ase_update_library(Iv[q], (double) glf[q], (double) elf[q]);
-                continue;
+                return;
             }
 #pragma unroll
             for (int q = 0; q < KS; q++) {
@@ -688,6 +671,32 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
                     Iv[q] = small[q] ? a : b;
                 }
             }
+        };
+        auto fetch = [&](int j, uint4 &e, float (&g)[KS]) {
+            e = slab_load(j);
+            const float *row = reinterpret_cast<const float *>(((unsigned long long) e.w << 32) | e.z);
+#pragma unroll
+            for (int q = 0; q < KS; q++)
+                g[q] = __ldg(row + koff[q]);
+        };
+        // Two records per trip with ping-pong registers: the row of the next record is
+        // requested before the current one is integrated, without rotating registers.
+        uint4 eA, eB;
+        float gA[KS], gB[KS];
+        fetch(0, eA, gA);
+        for (int j = 0;; j += 2) {
+            const bool haveB = j + 1 < cnt;
+            if (haveB)
+                fetch(j + 1, eB, gB);
+            update(__uint_as_float(eA.x), __uint_as_float(eA.y), gA);
+            if (!haveB)
+                break;
+            const bool haveA = j + 2 < cnt;
+            if (haveA)
+                fetch(j + 2, eA, gA);
+            update(__uint_as_float(eB.x), __uint_as_float(eB.y), gB);
+            if (!haveA)
+                break;
         }
     }
     bool neg = false, nan = false;
