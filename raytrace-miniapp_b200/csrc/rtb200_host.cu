@@ -89,8 +89,10 @@ struct rtb200_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     // staging
-    PinBuf h_blob;
-    DevBuf<char> d_blob;
+    PinBuf h_blob, h_gv;
+    DevBuf<char> d_blob, d_gv; // d_gv: the lineshape tables (read by the integration only)
+    const rtb200_problem *gv_pending = nullptr; // tables not filled/uploaded yet (create_image)
+    size_t gv_bytes = 0;
     DevProblem prob;
     bool staged = false;
     bool owner_ok = false; // ASE owner kernel usable (identity-like, injective pixel map)
@@ -114,8 +116,8 @@ struct rtb200_ctx {
     std::vector<cudaEvent_t> ev;
     size_t ev_used = 0;
     std::vector<std::pair<size_t, size_t>> ev_march, ev_integ; // (start, stop) indices
-    std::pair<size_t, size_t> ev_h2d{ 0, 0 }, ev_d2h{ 0, 0 };
-    bool have_h2d = false, have_d2h = false;
+    std::pair<size_t, size_t> ev_h2d{ 0, 0 }, ev_h2d_gv{ 0, 0 }, ev_d2h{ 0, 0 };
+    bool have_h2d = false, have_h2d_gv = false, have_d2h = false;
     rtb200_timings last;
     int launches = 0;
     bool count_steps = false;
@@ -144,7 +146,7 @@ void reset_timing(rtb200_ctx *ctx)
     ctx->ev_used = 0;
     ctx->ev_march.clear();
     ctx->ev_integ.clear();
-    ctx->have_h2d = ctx->have_d2h = false;
+    ctx->have_h2d = ctx->have_h2d_gv = ctx->have_d2h = false;
     ctx->launches = 0;
 }
 
@@ -161,6 +163,8 @@ void collect_timing(rtb200_ctx *ctx)
     std::memset(&t, 0, sizeof(t));
     if (ctx->have_h2d)
         t.h2d_ms = ev_ms(ctx, ctx->ev_h2d);
+    if (ctx->have_h2d_gv)
+        t.h2d_ms += ev_ms(ctx, ctx->ev_h2d_gv);
     if (ctx->have_d2h)
         t.d2h_ms = ev_ms(ctx, ctx->ev_d2h);
     for (auto &p : ctx->ev_march)
@@ -255,19 +259,46 @@ bool injective(const int *t, int n, int range)
     return true;
 }
 
+// Fills and uploads the lineshape tables if that is still pending (see stage_impl).
+int flush_gv(rtb200_ctx *ctx, cudaStream_t st)
+{
+    if (!ctx->gv_pending)
+        return RTB200_OK;
+    pack_gv(*ctx->gv_pending, ctx->h_gv.p);
+    ctx->gv_pending = nullptr;
+    ctx->ev_h2d_gv.first = new_event(ctx, st);
+    RTB_CUDA(cudaMemcpyAsync(ctx->d_gv.p, ctx->h_gv.p, ctx->gv_bytes, cudaMemcpyHostToDevice, st));
+    ctx->ev_h2d_gv.second = new_event(ctx, st);
+    ctx->have_h2d_gv = true;
+    return RTB200_OK;
+}
+
+// defer_gv: leave the lineshape tables (most of the bytes, not needed by the march) to
+// flush_gv(), which the caller runs on the host while the march kernel is already executing.
 int stage_impl(rtb200_ctx *ctx, const rtb200_problem *p, bool explicit_rays, int method,
-               double scale)
+               double scale, bool defer_gv = false)
 {
     RTB_CUDA(cudaSetDevice(ctx->device));
     DevProblem tmp;
-    const size_t bytes = pack_problem(*p, explicit_rays, method, scale, nullptr, nullptr, tmp);
+    GvBlob gvb{ nullptr, nullptr, false, 0 };
+    const size_t bytes = pack_problem(*p, explicit_rays, method, scale, nullptr, nullptr, tmp, &gvb);
     RTB_CUDA(ctx->h_blob.reserve(bytes));
     RTB_CUDA(ctx->d_blob.reserve(bytes));
-    pack_problem(*p, explicit_rays, method, scale, ctx->h_blob.p, ctx->d_blob.p, ctx->prob);
+    RTB_CUDA(ctx->h_gv.reserve(gvb.bytes));
+    RTB_CUDA(ctx->d_gv.reserve(gvb.bytes));
+    gvb.host = ctx->h_gv.p;
+    gvb.dev = ctx->d_gv.p;
+    gvb.copy = !defer_gv;
+    pack_problem(*p, explicit_rays, method, scale, ctx->h_blob.p, ctx->d_blob.p, ctx->prob, &gvb);
+    ctx->gv_bytes = gvb.bytes;
+    ctx->gv_pending = defer_gv ? p : nullptr;
     ctx->ev_h2d.first = new_event(ctx, ctx->stream);
     RTB_CUDA(cudaMemsetAsync(ctx->d_fail, 0, sizeof(FailState), ctx->stream));
     RTB_CUDA(cudaMemcpyAsync(ctx->d_blob.p, ctx->h_blob.p, bytes, cudaMemcpyHostToDevice,
                              ctx->stream));
+    if (!defer_gv)
+        RTB_CUDA(cudaMemcpyAsync(ctx->d_gv.p, ctx->h_gv.p, gvb.bytes, cudaMemcpyHostToDevice,
+                                 ctx->stream));
     ctx->ev_h2d.second = new_event(ctx, ctx->stream);
     ctx->have_h2d = true;
     ctx->staged = true;
@@ -309,6 +340,9 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
     if (pix1 <= pix0)
         return RTB200_OK;
     if (ctx->owner_ok && !out.Iv && !out.error && ctx->use_fused && row_stride == 1) {
+        int rg = flush_gv(ctx, st);
+        if (rg)
+            return rg;
         const size_t e0 = new_event(ctx, st);
         if (launch_trace_ase_fused(P, pix0, pix1, out, st)) {
             const size_t e1 = new_event(ctx, st);
@@ -339,13 +373,17 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
         c.row_stride = row_stride;
         const size_t e0 = new_event(ctx, st);
         launch_march(P, c, false, h, ctx->d_fail, ctx->count_steps, st, ctx->d_work, ctx->flat_march, ctx->march_blocks);
+        const size_t e1m = new_event(ctx, st);
+        rc = flush_gv(ctx, st); // host packs the lineshape tables while the march runs
+        if (rc)
+            return rc;
         const size_t e1 = new_event(ctx, st);
         if (ctx->owner_ok && !out.Iv && !out.error && P.K <= 128) // one pass of <= 4 bin slots
             launch_integrate_ase_owner(P, c, h, out, st);
         else
             launch_integrate_scatter(P, c, false, h, out, st);
         const size_t e2 = new_event(ctx, st);
-        ctx->ev_march.push_back({ e0, e1 });
+        ctx->ev_march.push_back({ e0, e1m });
         ctx->ev_integ.push_back({ e1, e2 });
         ctx->launches += 2;
     }
@@ -452,6 +490,8 @@ void rtb200_destroy(rtb200_ctx *ctx)
         cudaStreamSynchronize(ctx->stream);
     ctx->h_blob.release();
     ctx->d_blob.release();
+    ctx->h_gv.release();
+    ctx->d_gv.release();
     ctx->d_seg.release();
     ctx->d_meta.release();
     ctx->d_exit.release();
@@ -584,7 +624,7 @@ int rtb200_create_image(rtb200_ctx *ctx, const rtb200_problem *problem, unsigned
         return rc;
     reset_timing(ctx);
     new_event(ctx, ctx->stream);
-    rc = stage_impl(ctx, problem, false, 0, 0.0);
+    rc = stage_impl(ctx, problem, false, 0, 0.0, true);
     if (rc)
         return rc;
     const DevProblem &P = ctx->prob;
@@ -595,8 +635,13 @@ int rtb200_create_image(rtb200_ctx *ctx, const rtb200_problem *problem, unsigned
     RTB_CUDA(cudaMemsetAsync(ctx->d_iang.p, 0, n_ang * sizeof(double), ctx->stream));
     Outputs out{ ctx->d_image.p, ctx->d_iang.p, nullptr, nullptr, ctx->d_fail };
     rc = launch_pixels(ctx, 0, ctx->staged_pixels, out, ctx->stream);
-    if (rc)
+    if (rc == RTB200_OK)
+        rc = flush_gv(ctx, ctx->stream); // nothing was launched (no source pixels): finish the staging
+    ctx->gv_pending = nullptr;
+    if (rc) {
+        ctx->staged = false; // the tables may not have been uploaded
         return rc;
+    }
     ctx->ev_d2h.first = new_event(ctx, ctx->stream);
     RTB_CUDA(cudaMemcpyAsync(image, ctx->d_image.p, n_img * sizeof(double), cudaMemcpyDeviceToHost,
                              ctx->stream));

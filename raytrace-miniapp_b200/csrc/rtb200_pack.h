@@ -190,13 +190,27 @@ private:
     size_t off_;
 };
 
+// The lineshape tables gv[cell][k] are nine tenths of the blob and only the integration reads
+// them, so they can live in a second blob that is filled and uploaded while the march is already
+// running (rtb200_host.cu).  `bytes` is set by every pass; with `copy` false the arrays are only
+// laid out and pack_gv() fills them later.
+struct GvBlob {
+    char *host;
+    const char *dev;
+    bool copy;
+    size_t bytes;
+};
+
 // Packs `p` into the blob.  Returns the number of bytes used; fills `out` (pointers relative
 // to dev_base).  explicit_rays: the ray list comes separately (rtb200_trace_rays), so only the
 // planes, the destination grid and dv are packed and method/scale are given by the caller.
+// gvb == nullptr keeps the lineshape tables inside the main blob.
 inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int method_in,
-                           double scale_in, char *host, const char *dev_base, DevProblem &out)
+                           double scale_in, char *host, const char *dev_base, DevProblem &out,
+                           GvBlob *gvb = nullptr)
 {
     Blob blob(host, dev_base);
+    Blob gv_blob(gvb ? gvb->host : nullptr, gvb ? gvb->dev : nullptr);
     const bool fill = blob.filling();
     const rtb200_beam &e = *p.euv_beam;
     const int N = p.N, K = e.nv;
@@ -223,7 +237,9 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
         double *x = blob.alloc<double>((size_t) g.Nx, &P.x);
         double *y = blob.alloc<double>((size_t) g.Ny, &P.y);
         Node *node = blob.alloc<Node>(nn, &P.node);
-        float *gv = blob.alloc<float>(nn * (size_t) K, &P.gv);
+        float *gv = (gvb ? gv_blob : blob).alloc<float>(nn * (size_t) K, &P.gv);
+        if (gvb)
+            gvb->bytes = gv_blob.size();
         double *rwx = blob.alloc<double>((size_t) g.Nx, &P.rwx);
         double *rdx = blob.alloc<double>((size_t) g.Nx, &P.rdx);
         double *rwy = blob.alloc<double>((size_t) g.Ny, &P.rwy);
@@ -232,7 +248,9 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
         AxisCell *cy = blob.alloc<AxisCell>((size_t) g.Ny, &P.cy);
         if (fill) {
             bool ok = true;
-            auto recip = [&ok](const double *c, int n, double *rw, double *rd) {
+            double last_w = 0.0;
+            bool last_ok = false;
+            auto recip = [&](const double *c, int n, double *rw, double *rd) {
                 rw[0] = rd[0] = 0.0;
                 for (int k = 1; k < n; k++) {
                     const double w = c[k] - c[k - 1];
@@ -240,7 +258,12 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
                     rd[k] = 1.0 / (double) (float) w;
                     ok = ok && std::isnormal(rw[k]) && std::isnormal(rd[k]) && std::isnormal(w);
                     // every numerator must divide exactly through the tabulated reciprocal
-                    ok = ok && markstein_safe(w) && markstein_safe((double) (float) w);
+                    // (neighbouring cells of a grid mostly share their width: test it once)
+                    if (w != last_w) {
+                        last_ok = markstein_safe(w) && markstein_safe((double) (float) w);
+                        last_w = w;
+                    }
+                    ok = ok && last_ok;
                 }
             };
             recip(g.x, g.Nx, rwx, rdx);
@@ -255,7 +278,8 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
                 node[q].g0 = g.g0[q];
                 node[q].E0 = g.E0 ? g.E0[q] : 0.0f;
             }
-            std::memcpy(gv, g.gv, sizeof(float) * nn * (size_t) K);
+            if (gv && (!gvb || gvb->copy))
+                std::memcpy(gv, g.gv, sizeof(float) * nn * (size_t) K);
             P.Nx = g.Nx;
             P.Ny = g.Ny;
             P.range[0] = (float) g.x[0]; // :445-453
@@ -397,6 +421,20 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
         }
     }
     return blob.size();
+}
+
+// Fills a GvBlob that pack_problem laid out with copy == false (same allocation sequence).
+inline void pack_gv(const rtb200_problem &p, char *host)
+{
+    Blob gv_blob(host, host);
+    const int K = p.euv_beam->nv;
+    for (int ii = 0; ii < p.N; ii++) {
+        const rtb200_gain_plane &g = p.gain[ii];
+        const size_t n = (size_t) g.Nx * g.Ny * (size_t) K;
+        const float *unused;
+        float *gv = gv_blob.alloc<float>(n, &unused);
+        std::memcpy(gv, g.gv, sizeof(float) * n);
+    }
 }
 
 } // namespace rtb
