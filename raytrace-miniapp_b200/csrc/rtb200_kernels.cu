@@ -802,7 +802,11 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, RTB_OWNER_MINBLOCKS)
         pix[q] = 0.0;
         const int k = lane + 32 * q;
         dv2[q] = k < K ? __ldg(&P.dv2[k]) : 0.0;
-        koff[q] = min(k, K - 1); // lanes past the last bin recompute bin K-1 (never stored)
+        // Lanes past the last bin recompute a bin that another lane of the SAME slot already
+        // holds (never stored): duplicates cannot add a branch to the slot's flag set, whereas
+        // a fixed bin K-1 (far wing, Taylor branch) made the last slot take both branches.
+        const int live = K - 32 * q; // bins of this slot
+        koff[q] = k < K ? k : (live > 0 ? 32 * q + (k - K) % live : K - 1);
     }
     const PinnedConsts KC(P.kfp_g, exp_tab);
     const unsigned slab_addr =
