@@ -123,6 +123,7 @@ struct rtb200_ctx {
     bool count_steps = false;
     bool use_fused = false; // opt-in (RTB200_FUSED=1): measured slower than the two-kernel path
     bool flat_march = true;
+    bool ieee_div = false; // never take the reciprocal-table division path (ddiv_by)
     int march_blocks = 0; // grid of the persistent march on this device
     unsigned long long *d_work = nullptr;
     size_t handoff_bytes = (size_t) 4096 << 20; // B200 has 180 GB: one chunk for every shipped / synthetic size
@@ -292,6 +293,11 @@ int stage_impl(rtb200_ctx *ctx, const rtb200_problem *p, bool explicit_rays, int
     pack_problem(*p, explicit_rays, method, scale, ctx->h_blob.p, ctx->d_blob.p, ctx->prob, &gvb);
     ctx->gv_bytes = gvb.bytes;
     ctx->gv_pending = defer_gv ? p : nullptr;
+    if (ctx->ieee_div) {
+        DevPlane *hp = reinterpret_cast<DevPlane *>(ctx->h_blob.p + ((const char *) ctx->prob.planes - ctx->d_blob.p));
+        for (int i = 0; i < ctx->prob.N; i++)
+            hp[i].fast_div = 0;
+    }
     ctx->ev_h2d.first = new_event(ctx, ctx->stream);
     RTB_CUDA(cudaMemsetAsync(ctx->d_fail, 0, sizeof(FailState), ctx->stream));
     RTB_CUDA(cudaMemcpyAsync(ctx->d_blob.p, ctx->h_blob.p, bytes, cudaMemcpyHostToDevice,
@@ -477,6 +483,8 @@ int rtb200_create(int device, rtb200_ctx **out)
         ctx->use_fused = atoi(s) != 0;
     if (const char *s = getenv("RTB200_FLAT_MARCH"))
         ctx->flat_march = atoi(s) != 0;
+    if (const char *s = getenv("RTB200_IEEE_DIV")) // tests: plain IEEE divisions by the cell widths
+        ctx->ieee_div = atoi(s) != 0;
     *out = ctx;
     return RTB200_OK;
 }

@@ -84,6 +84,16 @@ def resample_gain(g, fx, fy):
                 bil(g.gv).astype(np.float32), bil(g.gv0).astype(np.float32))
 
 
+def warp_gain_grid(g, ax=0.6, ay=-0.5):
+    """Same node data on a NON-uniform grid: u -> u + a*u*(1-u) on each axis (monotone for
+    |a| < 1, end points fixed).  Exercises the generic cell search and cell widths that all
+    differ (the reference's findindex is a bisection, any monotone grid is legal)."""
+    def warp(c, a):
+        u = (c - c[0]) / (c[-1] - c[0])
+        return c[0] + (c[-1] - c[0]) * (u + a * u * (1.0 - u))
+    return Gain(warp(g.x, ax), warp(g.y, ay), g.n, g.g0, g.E0, g.gv, g.gv0)
+
+
 def s4(small, gain_factor=2, image_factor=2):
     """Config 4: gain planes resampled to gain_factor x finer cells per axis, image nx, ny x
     image_factor, angles unchanged."""

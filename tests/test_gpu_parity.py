@@ -223,12 +223,13 @@ def test_ray_trajectories(ase_small, seed_small, oracle, ctx):
             assert np.array_equal(g["x"], ref[:, :, 0]) and np.array_equal(g["y"], ref[:, :, 1])
 
 
-@pytest.mark.parametrize("env", [{"RTB200_FLAT_MARCH": "0"}, {"RTB200_FUSED": "1"}, {"RTB200_HANDOFF_MB": "8"}],
-                         ids=["nested-march", "fused-kernel", "small-handoff-chunks"])
+@pytest.mark.parametrize("env", [{"RTB200_FLAT_MARCH": "0"}, {"RTB200_FUSED": "1"}, {"RTB200_HANDOFF_MB": "8"},
+                                 {"RTB200_IEEE_DIV": "1"}],
+                         ids=["nested-march", "fused-kernel", "small-handoff-chunks", "ieee-divisions"])
 def test_alternative_kernel_paths(env, ase_small, rtlib, monkeypatch):
     """The literal nested march kernel, the opt-in fused kernel and a hand-off arena that forces
     many chunks give the same image as the default path (bit for bit: same march, same per-pixel
-    summation order)."""
+    summation order); so do plain IEEE divisions in place of the reciprocal-table divisions."""
     p, extra = ase_small
     base = rtlib.Context(0)
     img0, ang0 = base.create_image(p)
@@ -242,3 +243,62 @@ def test_alternative_kernel_paths(env, ase_small, rtlib, monkeypatch):
     if "RTB200_FUSED" not in env:  # the fused kernel sums a pixel's rays in another order
         assert np.array_equal(img0, img1)
     assert rel_l2(img1, img0) < 1e-14
+
+
+def _warped(p):
+    from raytrace_miniapp_b200 import synth
+    q = abi.Problem(p.euv_beam, [p.gain[0]] + [synth.warp_gain_grid(g) for g in p.gain[1:]],
+                    p.seed_beam, p.seed, p.N_start, p.N_parallel)
+    return q
+
+
+def test_non_uniform_gain_grid(ase_small, oracle, ctx, rtlib, monkeypatch):
+    """Gain planes on a non-uniform (x, y) grid: every cell has its own width, the index guess of
+    the interval table is wrong for most cells (generic search), and the reciprocal-table
+    divisions meet ~130 distinct divisors per plane.  March bit-exact, image within tolerance,
+    and identical bits with IEEE divisions."""
+    p = _warped(ase_small[0])
+    assert np.unique(np.diff(p.gain[1].x).round(12)).size > 50
+    rays = p.rays()[11::97]
+    g = ctx.calc_rays(p, rays)
+    o = oracle.calc_rays(p, rays)
+    assert np.array_equal(g["error"], o["error"]) and (o["error"] == 0).sum() > 1000
+    for f in ("gvl", "evl"):
+        assert np.array_equal(g[f].view(np.uint32), o[f].view(np.uint32)), f
+    assert np.array_equal(g["ivl"], o["ivl"])
+    p.N_start, p.N_parallel = 5, 19
+    img, ang = ctx.create_image(p)
+    oi = oracle.create_image(p)
+    assert np.linalg.norm(oi["image"]) > 0
+    check_image((img, ang), (oi["image"], oi["I_ang"]))
+    monkeypatch.setenv("RTB200_IEEE_DIV", "1")
+    alt = rtlib.Context(0)
+    g2 = alt.calc_rays(p, rays)
+    img2, ang2 = alt.create_image(p)
+    alt.close()
+    for f in ("gvl", "evl"):
+        assert np.array_equal(g[f].view(np.uint32), g2[f].view(np.uint32)), f
+    assert np.array_equal(img, img2)
+    assert rel_l2(ang, ang2) < 1e-13  # I_ang is summed with FP64 atomics: order varies run to run
+
+
+def test_vacuum_planes_and_empty_inputs(ase_small, oracle, ctx):
+    """Zero gain and emission in one plane (identity records on the integration side) and the
+    empty cases of the explicit-ray entry points."""
+    p0 = ase_small[0]
+    planes = list(p0.gain)
+    for i in (1,):
+        g = planes[i]
+        planes[i] = abi.Gain(g.x, g.y, g.n, np.zeros_like(g.g0), np.zeros_like(g.E0), g.gv, g.gv0)
+    p = abi.Problem(p0.euv_beam, planes, None, None, 3, 31)
+    img, ang = ctx.create_image(p)
+    o = oracle.create_image(p)
+    assert np.linalg.norm(o["image"]) > 0
+    check_image((img, ang), (o["image"], o["I_ang"]))
+    none = p.rays()[:0]
+    g = ctx.calc_rays(p, none)
+    assert g["error"].size == 0 and g["Iv"].shape[0] == 0
+    img0 = np.zeros_like(img)
+    ang0 = np.zeros_like(ang)
+    ctx.trace_rays(p, none, p.method, 1.0, img0.ravel(), ang0.ravel())
+    assert not img0.any() and not ang0.any()
