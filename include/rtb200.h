@@ -206,6 +206,16 @@ void rtb200_free_problem(rtb200_problem *problem);
  * instructions * 32 lanes per second, i.e. FP64 lane-instr/s) of the context's device. */
 int rtb200_measure_fp64_peak(rtb200_ctx *ctx, double *fp64_lane_instr_per_s);
 
+/* Proof by exhaustion for the march's branch-free FP32 division (csrc/rtb200_math.cuh,
+ * fdiv_refined): compares it with the IEEE division on the device for the divisor significands
+ * [b_first, b_first + b_count) (of 2^23) times ALL 2^23 numerator significands, operands scaled
+ * by 2^exp_a / 2^exp_b (-60 <= exp < 60).  Returns the number of differing quotients and one
+ * offending pair.  The whole significand space takes about 75 s on a B200.  variant 0 is the
+ * division the march uses; variant 1 omits its correction step (a self-test of the detector:
+ * it must report mismatches). */
+int rtb200_check_fdiv(rtb200_ctx *ctx, unsigned b_first, unsigned b_count, int exp_a, int exp_b,
+                      int variant, unsigned long long *mismatches, float *witness_a, float *witness_b);
+
 #ifdef __cplusplus
 }
 #endif

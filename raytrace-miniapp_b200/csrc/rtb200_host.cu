@@ -1025,4 +1025,28 @@ int rtb200_measure_fp64_peak(rtb200_ctx *ctx, double *rate)
     return RTB200_OK;
 }
 
+int rtb200_check_fdiv(rtb200_ctx *ctx, unsigned b_first, unsigned b_count, int exp_a, int exp_b,
+                      int variant, unsigned long long *mismatches, float *witness_a, float *witness_b)
+{
+    if (!ctx || !mismatches || b_first >= (1u << 23) || b_count > (1u << 23) - b_first ||
+        exp_a < -60 || exp_a > 59 || exp_b < -60 || exp_b > 59)
+        return RTB200_ERR_ARG;
+    RTB_CUDA(cudaSetDevice(ctx->device));
+    RTB_CUDA(ctx->d_Iv.reserve(16));
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(ctx->d_Iv.p);
+    RTB_CUDA(cudaMemsetAsync(d, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    launch_fdiv_check(b_first, b_count, exp_a, exp_b, variant, d, ctx->stream);
+    unsigned long long h[3] = { 0, 0, 0 };
+    RTB_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    RTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    RTB_CUDA(cudaGetLastError());
+    *mismatches = h[0];
+    const unsigned ab = (unsigned) h[1], bb = (unsigned) h[2];
+    if (witness_a)
+        std::memcpy(witness_a, &ab, 4);
+    if (witness_b)
+        std::memcpy(witness_b, &bb, 4);
+    return RTB200_OK;
+}
+
 } // extern "C"

@@ -1589,6 +1589,48 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters)
         out[0] = r; // never true; keeps the chains alive
 }
 
+// ------------------------------------------------------------------------------------------
+// Exhaustive check of fdiv_refined against the correctly rounded quotient: divisor significands [b_first, b_first +
+// b_count) x ALL 2^23 numerator significands, at binary exponents ea / eb.  One thread per
+// (divisor, 128 consecutive numerators).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fdiv_check_kernel(unsigned b_first, unsigned b_count, int ea, int eb, int variant,
+                                                         unsigned long long *out /* [0] mismatches, [1] a bits, [2] b bits */)
+{
+    const unsigned long long tid = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long total = (unsigned long long) b_count << 16; // 2^23 / 128 numerator groups
+    unsigned long long bad = 0;
+    for (unsigned long long w = tid; w < total; w += (unsigned long long) gridDim.x * blockDim.x) {
+        const unsigned bm = b_first + (unsigned) (w >> 16);
+        const unsigned a0 = (unsigned) (w & 0xffffu) << 7;
+        const float b = __uint_as_float(((unsigned) (eb + 127) << 23) | (bm & 0x7fffffu));
+        const float r = frcp_refined(b);
+#pragma unroll 4
+        for (unsigned i = 0; i < 128u; i++) {
+            const float a = __uint_as_float(((unsigned) (ea + 127) << 23) | (a0 + i));
+            // Independent oracle: the FP64 quotient rounded to float.  53 >= 2*24 + 2 bits, so the
+            // double rounding is innocuous and this IS the correctly rounded float quotient
+            // (comparing with __fdiv_rn would compare the sequence with itself).
+            // variant 1 (detector self-test): the uncorrected product a*r, which is only faithful
+            const float q = variant == 1 ? __fmul_rn(a, r) : fdiv_refined(a, b, r);
+            const float want = __double2float_rn(__ddiv_rn((double) a, (double) b));
+            if (__float_as_uint(q) != __float_as_uint(want)) {
+                bad++;
+                out[1] = __float_as_uint(a);
+                out[2] = __float_as_uint(b);
+            }
+        }
+    }
+    if (bad)
+        atomicAdd(&out[0], bad);
+}
+
+void launch_fdiv_check(unsigned b_first, unsigned b_count, int ea, int eb, int variant,
+                       unsigned long long *out, cudaStream_t st)
+{
+    fdiv_check_kernel<<<148 * 16, 256, 0, st>>>(b_first, b_count, ea, eb, variant, out);
+}
+
 // Grid of the persistent march: resident CTAs per SM (occupancy) x SMs of the current device.
 int march_persistent_blocks()
 {

@@ -54,5 +54,7 @@ bool launch_trace_ase_fused(const DevProblem &P, long long pix0, long long pix1,
 void launch_path_intensity(const DevProblem &P, const Chunk &c, const Handoff &h, float *path_I,
                            int *error, cudaStream_t st);
 void launch_fp64_peak(double *out, int iters, cudaStream_t st, int *blocks, int *threads);
+void launch_fdiv_check(unsigned b_first, unsigned b_count, int ea, int eb, int variant,
+                       unsigned long long *out, cudaStream_t st);
 
 } // namespace rtb

@@ -87,6 +87,8 @@ def load():
     L.rtb200_free_problem.argtypes = [P(abi.CProblem)]
     L.rtb200_free_problem.restype = None
     L.rtb200_measure_fp64_peak.argtypes = [ctx, P(C.c_double)]
+    L.rtb200_check_fdiv.argtypes = [ctx, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, P(C.c_ulonglong),
+                                    P(C.c_float), P(C.c_float)]
     _LIB = L
     return L
 
@@ -278,6 +280,14 @@ class Context:
         t = abi.Timings()
         self._check(self.L.rtb200_get_timings(self.h, C.byref(t)))
         return {k: getattr(t, k) for k, _ in abi.Timings._fields_ if k != "reserved"}
+
+    def check_fdiv(self, b_first, b_count, exp_a=0, exp_b=0, variant=0):
+        """Mismatches of the branch-free FP32 division against IEEE over b_count divisor
+        significands x all 2^23 numerator significands; returns (count, a, b)."""
+        n, a, b = C.c_ulonglong(0), C.c_float(0), C.c_float(0)
+        self._check(self.L.rtb200_check_fdiv(self.h, b_first, b_count, exp_a, exp_b, variant, C.byref(n),
+                                             C.byref(a), C.byref(b)))
+        return n.value, a.value, b.value
 
     def measure_fp64_peak(self):
         r = C.c_double(0)
