@@ -1219,8 +1219,11 @@ __device__ double dev_calc_seed(const DevProblem &P, double x, double y, double 
 
 // One warp per ray slot; K is covered in passes of 32*KS bins (one pass for K <= 128).  Handles both integration modes,
 // both ray sources, scatter binning and the per-ray dumps.
+#ifndef RTB_SCATTER_MINBLOCKS
+#define RTB_SCATTER_MINBLOCKS 3
+#endif
 template <bool LIST, int KS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
     integrate_scatter_kernel(const DevProblem P, const Chunk c, const Handoff h, const Outputs o)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1273,18 +1276,39 @@ __global__ void __launch_bounds__(256)
         acc_w = 0.0;
         cur_bin = -1;
     };
-    const long long n_runs = (n_slots + RUN - 1) / RUN;
-    for (long long run = warp_id; run < n_runs; run += n_warps) {
-    const long long slot_end = (run + 1) * RUN < n_slots ? (run + 1) * RUN : n_slots;
-    for (long long slot = run * RUN; slot < slot_end; slot++) {
-        const unsigned meta = __ldg(&h.meta[slot]);
-        if (meta & RTB_META_INACTIVE)
-            continue;
-        float rx, ry, ra, rb;
-        double f = 0.0; // seed amplitude
+    // The source coordinates of a slot (only needed again to report a failed ray).
+    auto slot_ray = [&](long long slot, float &rx, float &ry, float &ra, float &rb, int &pi, int &pj,
+                        int &ka, int &m) {
         if (LIST) {
             const float4 r = __ldg(&c.rays[c.ray0 + slot]);
             rx = r.x, ry = r.y, ra = r.z, rb = r.w;
+            pi = pj = ka = m = 0;
+        } else {
+            const unsigned lq = (unsigned) slot / (unsigned) P.ab_max; // slots fit 32 bits
+            const long long p = phys_pixel(P, c, c.pix0 + lq);
+            const int t = (int) ((unsigned) slot - lq * (unsigned) P.ab_max);
+            const PixelRays pr = pixel_rays(P, p);
+            const int ab = pr.ab0 + t * (int) P.n_parallel;
+            ka = (int) ((unsigned) ab / (unsigned) P.snb);
+            m = ab - ka * P.snb;
+            pi = pr.i;
+            pj = pr.j;
+            rx = __ldg(&P.sxf[pi]);
+            ry = __ldg(&P.syf[pj]);
+            ra = __ldg(&P.saf[ka]);
+            rb = __ldg(&P.sbf[m]);
+        }
+    };
+    // Everything about a ray slot that is the same for all frequency bins: the seed amplitude
+    // and the destination pixel / angular bin.  Evaluated by ONE lane per slot, 32 slots at a
+    // time, and handed to the warp by shuffles (it used to be repeated by all 32 lanes of the
+    // warp for every ray: ~250 of ~800 instructions per ray).
+    auto prologue = [&](long long slot, unsigned meta, double &f, long long &pix, int &bin) {
+        float rx, ry, ra, rb;
+        int pi, pj, ka, m;
+        slot_ray(slot, rx, ry, ra, rb, pi, pj, ka, m);
+        f = 0.0;
+        if (LIST) {
             if (P.seed_fv && !(meta & (RTB_META_ESCAPED | RTB_META_INVALID))) {
                 if (P.method == 1) { // backward: seed at the exit point (:525-529)
                     const float4 e = h.exit_ray[slot];
@@ -1293,32 +1317,18 @@ __global__ void __launch_bounds__(256)
                     f = dev_calc_seed(P, (double) rx, (double) ry, (double) ra, (double) rb);
                 }
             }
-        } else {
-            const unsigned lq = (unsigned) slot / (unsigned) P.ab_max; // slots fit 32 bits
-            const long long p = phys_pixel(P, c, c.pix0 + lq);
-            const int t = (int) ((unsigned) slot - lq * (unsigned) P.ab_max);
-            const PixelRays pr = pixel_rays(P, p);
-            const int ab = pr.ab0 + t * (int) P.n_parallel;
-            const int ka = (int) ((unsigned) ab / (unsigned) P.snb), m = ab - ka * P.snb;
-            rx = __ldg(&P.sxf[pr.i]);
-            ry = __ldg(&P.syf[pr.j]);
-            ra = __ldg(&P.saf[ka]);
-            rb = __ldg(&P.sbf[m]);
-            if (P.seed_fx && !(meta & RTB_META_ESCAPED)) {
-                // calc_seed_inline (:230-247) from the per-index tables
-                const double fx = __ldg(&P.seed_fx[pr.i]), fy = __ldg(&P.seed_fy[pr.j]);
-                const double fa = __ldg(&P.seed_fa[ka]), fb = __ldg(&P.seed_fb[m]);
-                if (fx == fx && fy == fy && fa == fa && fb == fb) {
-                    f = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(P.seed_f0, fx), fy), fa), fb);
-                    f = f < 0.0 ? 0.0 : f;
-                }
+        } else if (P.seed_fx && !(meta & RTB_META_ESCAPED)) {
+            // calc_seed_inline (:230-247) from the per-index tables
+            const double fx = __ldg(&P.seed_fx[pi]), fy = __ldg(&P.seed_fy[pj]);
+            const double fa = __ldg(&P.seed_fa[ka]), fb = __ldg(&P.seed_fb[m]);
+            if (fx == fx && fy == fy && fa == fa && fb == fb) {
+                f = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(P.seed_f0, fx), fy), fa), fb);
+                f = f < 0.0 ? 0.0 : f;
             }
         }
-        const bool invalid = (meta & RTB_META_INVALID) != 0;
-        int code = invalid ? 1 : 0;
-        // destination cells
-        int i1 = -1, i2 = -1, i3 = -1, i4 = -1;
-        if (!invalid && (o.image || o.I_ang)) {
+        pix = -1;
+        bin = -1;
+        if (!(meta & RTB_META_INVALID) && (o.image || o.I_ang)) {
             float bx = rx, by = ry, ba = ra, bb = rb;
             if (P.method != 1) { // forward: bin by the exit ray (RayTraceImageCPU.cpp:40-49)
                 const float4 e = h.exit_ray[slot];
@@ -1329,19 +1339,48 @@ __global__ void __launch_bounds__(256)
                 if (by < 0.0f && P.y_mirror)
                     by = -by;
             }
-            // the four destination indices are independent: lanes 0..3 search one grid each
-            // (x, y, a, b) and the results are broadcast, instead of 32 lanes repeating all four
-            const int d = lane & 3;
-            const int nn = d == 0 ? P.nx : (d == 1 ? P.ny : (d == 2 ? P.na : P.nb));
-            const double *xx = d == 0 ? P.ex : (d == 1 ? P.ey : (d == 2 ? P.ea : P.eb));
-            const double dd = d == 0 ? P.edx : (d == 1 ? P.edy : (d == 2 ? P.eda : P.edb));
-            const float yy = d == 0 ? bx : (d == 1 ? by : (d == 2 ? ba : bb));
-            const int idx = dev_get_index(nn, xx, dd, (double) yy);
-            i1 = __shfl_sync(0xffffffffu, idx, 0);
-            i2 = __shfl_sync(0xffffffffu, idx, 1);
-            i3 = __shfl_sync(0xffffffffu, idx, 2);
-            i4 = __shfl_sync(0xffffffffu, idx, 3);
+            const int i1 = dev_get_index(P.nx, P.ex, P.edx, (double) bx);
+            const int i2 = dev_get_index(P.ny, P.ey, P.edy, (double) by);
+            const int i3 = dev_get_index(P.na, P.ea, P.eda, (double) ba);
+            const int i4 = dev_get_index(P.nb, P.eb, P.edb, (double) bb);
+            if (o.image && i1 >= 0 && i2 >= 0)
+                pix = (long long) i1 + (long long) i2 * P.nx;
+            if (i3 >= 0 && i4 >= 0)
+                bin = i3 + i4 * P.na;
         }
+    };
+    // seed spectrum of this lane's bins (single pass over the bins)
+    double fv[KS];
+#pragma unroll
+    for (int q = 0; q < KS; q++) {
+        const int k = lane + 32 * q;
+        fv[q] = (combine && P.seed_fv && k < K) ? __ldg(&P.seed_fv[k]) : 0.0;
+    }
+    const long long n_runs = (n_slots + RUN - 1) / RUN;
+    for (long long run = warp_id; run < n_runs; run += n_warps) {
+    const long long slot_end = (run + 1) * RUN < n_slots ? (run + 1) * RUN : n_slots;
+    for (long long base = run * RUN; base < slot_end; base += 32) {
+    unsigned meta_l = RTB_META_INACTIVE;
+    double f_l = 0.0;
+    long long pix_l = -1;
+    int bin_l = -1;
+    if (base + lane < slot_end) {
+        meta_l = __ldg(&h.meta[base + lane]);
+        if (!(meta_l & RTB_META_INACTIVE))
+            prologue(base + lane, meta_l, f_l, pix_l, bin_l);
+    }
+    __syncwarp();
+    const int n_here = (int) (slot_end - base < 32 ? slot_end - base : 32);
+    for (int j = 0; j < n_here; j++) {
+        const long long slot = base + j;
+        const unsigned meta = __shfl_sync(0xffffffffu, meta_l, j);
+        if (meta & RTB_META_INACTIVE)
+            continue;
+        const double f = __shfl_sync(0xffffffffu, f_l, j);
+        const long long pix = __shfl_sync(0xffffffffu, pix_l, j);
+        const int bin = __shfl_sync(0xffffffffu, bin_l, j);
+        const bool invalid = (meta & RTB_META_INVALID) != 0;
+        int code = invalid ? 1 : 0;
         double w = 0.0;
         bool bad = false;
         for (int kbase = 0; kbase < K && !bad; kbase += 32 * KS) {
@@ -1349,7 +1388,10 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
             for (int q = 0; q < KS; q++) {
                 const int k = kbase + lane + 32 * q;
-                Iv[q] = (f != 0.0 && k < K) ? __dmul_rn(f, __ldg(&P.seed_fv[k])) : 0.0;
+                if (combine)
+                    Iv[q] = f != 0.0 ? __dmul_rn(f, fv[q]) : 0.0; // fv = 0 for k >= K
+                else
+                    Iv[q] = (f != 0.0 && k < K) ? __dmul_rn(f, __ldg(&P.seed_fv[k])) : 0.0;
             }
             if (!invalid) {
                 const int cc = gain_only
@@ -1371,8 +1413,6 @@ __global__ void __launch_bounds__(256)
             // several passes; with one pass (K <= 64) it happens right here.
             if (combine) {
                 if (code == 0 && !invalid) {
-                    const long long pix = (o.image && i1 >= 0 && i2 >= 0)
-                                              ? (long long) i1 + (long long) i2 * P.nx : -1;
                     if (pix != cur_pix) {
                         flush_pix();
                         cur_pix = pix;
@@ -1406,16 +1446,14 @@ __global__ void __launch_bounds__(256)
                     const int k = kbase + lane + 32 * q;
                     if (k < K) {
                         w += __ldg(&P.dv2[k]) * Iv[q];
-                        if (o.image && i1 >= 0 && i2 >= 0)
-                            atomicAdd(&o.image[(size_t) K * ((size_t) i1 + (size_t) i2 * P.nx) + k],
-                                      Iv[q] * P.scale);
+                        if (pix >= 0)
+                            atomicAdd(&o.image[(size_t) K * (size_t) pix + k], Iv[q] * P.scale);
                     }
                 }
             }
         }
         if (code == 0 && !invalid && o.I_ang) {
             w = warp_sum(w);
-            const int bin = (i3 >= 0 && i4 >= 0) ? i3 + i4 * P.na : -1;
             if (bin != cur_bin) {
                 flush_bin();
                 cur_bin = bin;
@@ -1425,9 +1463,14 @@ __global__ void __launch_bounds__(256)
         if (lane == 0) {
             if (o.error)
                 o.error[slot] = -code;
-            if (code >= 2)
+            if (code >= 2) {
+                float rx, ry, ra, rb;
+                int pi, pj, ka, m;
+                slot_ray(slot, rx, ry, ra, rb, pi, pj, ka, m);
                 report_failure(o.fail, code, rx, ry, ra, rb);
+            }
         }
+    }
     }
     flush_pix();
     flush_bin();
