@@ -811,34 +811,53 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, RTB_OWNER_MINBLOCKS)
     const PinnedConsts KC(P.kfp_g, exp_tab);
     const unsigned slab_addr =
         __shfl_sync(0xffffffffu, (unsigned) __cvta_generic_to_shared(&rec_slab[warp][0]), 0);
-    for (int t = warp; t < pr.cnt; t += RTB_OWNER_WARPS) {
-        const long long slot = slot0 + t;
-        const unsigned meta = __ldg(&h.meta[slot]);
-        if (meta & RTB_META_INVALID)
-            continue; // error -1, reported by the march
-        double Iv[KS];
-#pragma unroll
-        for (int q = 0; q < KS; q++)
-            Iv[q] = 0.0;
-        const int code =
-            integrate_ray_ase_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, koff, Iv, KC, slab_addr);
-        const int ab = pr.ab0 + t * (int) P.n_parallel;
-        const int ka = ab / P.snb, m = ab % P.snb;
-        if (code != 0) {
-            if (lane == 0)
-                report_failure(o.fail, code, P.sxf[pr.i], P.syf[pr.j], P.saf[ka], P.sbf[m]);
-            continue;
+    // The warp's rays are t = warp, warp + 8, ...; what is per ray and not per bin (hand-off meta
+    // word, angular bin) is looked up by one lane per ray, 32 rays at a time.
+    for (int t0 = warp; t0 < pr.cnt; t0 += 32 * RTB_OWNER_WARPS) {
+        unsigned meta_l = RTB_META_INVALID;
+        int bin_l = -1;
+        {
+            const int t = t0 + lane * RTB_OWNER_WARPS;
+            if (t < pr.cnt) {
+                meta_l = __ldg(&h.meta[slot0 + t]);
+                const int ab = pr.ab0 + t * (int) P.n_parallel;
+                const int ka = ab / P.snb, m = ab - ka * P.snb;
+                const int ba = __ldg(&P.binA[ka]), bb = __ldg(&P.binB[m]);
+                bin_l = (ba >= 0 && bb >= 0) ? ba + bb * P.na : -1;
+            }
         }
-        double w = 0.0;
+        const int n_here = min(32, (pr.cnt - t0 + RTB_OWNER_WARPS - 1) / RTB_OWNER_WARPS);
+        for (int j = 0; j < n_here; j++) {
+            const int t = t0 + j * RTB_OWNER_WARPS;
+            const long long slot = slot0 + t;
+            const unsigned meta = __shfl_sync(0xffffffffu, meta_l, j);
+            const int bin = __shfl_sync(0xffffffffu, bin_l, j);
+            if (meta & RTB_META_INVALID)
+                continue; // error -1, reported by the march
+            double Iv[KS];
 #pragma unroll
-        for (int q = 0; q < KS; q++) {
-            w += dv2[q] * Iv[q];
-            pix[q] += Iv[q] * P.scale;
+            for (int q = 0; q < KS; q++)
+                Iv[q] = 0.0;
+            const int code = integrate_ray_ase_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, koff, Iv, KC,
+                                                        slab_addr);
+            if (code != 0) {
+                if (lane == 0) {
+                    const int ab = pr.ab0 + t * (int) P.n_parallel;
+                    const int ka = ab / P.snb, m = ab % P.snb;
+                    report_failure(o.fail, code, P.sxf[pr.i], P.syf[pr.j], P.saf[ka], P.sbf[m]);
+                }
+                continue;
+            }
+            double w = 0.0;
+#pragma unroll
+            for (int q = 0; q < KS; q++) {
+                w += dv2[q] * Iv[q];
+                pix[q] += Iv[q] * P.scale;
+            }
+            w = warp_sum(w);
+            if (lane == 0 && bin >= 0)
+                atomicAdd(&o.I_ang[bin], w);
         }
-        w = warp_sum(w);
-        const int ba = __ldg(&P.binA[ka]), bb = __ldg(&P.binB[m]);
-        if (lane == 0 && ba >= 0 && bb >= 0)
-            atomicAdd(&o.I_ang[ba + bb * P.na], w);
     }
 #pragma unroll
     for (int q = 0; q < KS; q++)
