@@ -661,9 +661,9 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
                 const unsigned f = (flags >> (2 * q)) & 3u; // warp-uniform
                 // three straight-line variants: the common one (every lane of the slot on the
                 // exp branch) carries no select and no dead Taylor result
-                if (f == 2u) {
+                if (__builtin_expect(f == 2u, 1)) {
                     Iv[q] = ase_update_large(Iv[q], gl, el, rcp_approx(glf[q]), KC);
-                } else if (f == 1u) {
+                } else if (__builtin_expect(f == 1u, 0)) {
                     Iv[q] = ase_update_small(Iv[q], gl, el, KC);
                 } else {
                     const double a = ase_update_small(Iv[q], gl, el, KC);
