@@ -1289,9 +1289,12 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
         }
         cur_pix = -1;
     };
-    auto flush_bin = [&]() {
-        if (cur_bin >= 0 && lane == 0)
-            atomicAdd(&o.I_ang[cur_bin], acc_w);
+    auto flush_bin = [&]() { // acc_w: this lane's share of the run's angular-bin sum
+        if (cur_bin >= 0) {
+            const double w = warp_sum(acc_w);
+            if (lane == 0)
+                atomicAdd(&o.I_ang[cur_bin], w);
+        }
         acc_w = 0.0;
         cur_bin = -1;
     };
@@ -1472,8 +1475,7 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
             }
         }
         if (code == 0 && !invalid && o.I_ang) {
-            w = warp_sum(w);
-            if (bin != cur_bin) {
+            if (bin != cur_bin) { // one warp reduction per run of rays with the same bin
                 flush_bin();
                 cur_bin = bin;
             }
