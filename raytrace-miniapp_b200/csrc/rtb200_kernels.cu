@@ -268,6 +268,29 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
     float rx = 0.f, ry = 0.f, ra = 0.f, rb = 0.f;
     unsigned total_steps = 0;
     GlobalSinkT<PATH> sink{ h.seg, nullptr };
+    bool pending = false; // a marched ray whose hand-off entry has not been closed yet
+    // Closes the lane's finished ray: meta word, failure report, exit ray (the two atanf of the
+    // seeded path).  Runs at the lane's next refill, i.e. for RTB_REFILL_MIN or more lanes at a
+    // time, instead of right after the trip in which a single lane happened to finish.
+    auto finalize = [&]() {
+        unsigned meta = (unsigned) m.seg_lo | ((unsigned) m.seg_hi << 12);
+        if (m.escaped)
+            meta |= RTB_META_ESCAPED;
+        if (lt_0p01(fmul(m.s.z, m.s.z)) || m.steps > (1u << 22)) { // error -1 (:515-516)
+            meta |= RTB_META_INVALID;
+            report_failure(fail, 1, rx, ry, ra, rb);
+        } else if (h.exit_ray) {
+            float4 e;
+            e.x = m.pos.x;
+            e.y = m.pos.y;
+            e.z = fmul(atanf_fdlibm(fdiv(m.s.x, m.s.z)), 1e3f);
+            e.w = fmul(atanf_fdlibm(fdiv(m.s.y, m.s.z)), 1e3f);
+            h.exit_ray[L] = e;
+        }
+        h.meta[L] = meta;
+        total_steps += m.steps;
+        pending = false;
+    };
     for (;;) {
         const bool need = m.phase == PH_DONE && !dead;
         const unsigned want = __ballot_sync(0xffffffffu, need);
@@ -293,6 +316,8 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
             }
             const long long mine = run_next + __popc(want & ((1u << lane) - 1u));
             const long long after = run_next + __popc(want);
+            if (need && pending)
+                finalize();
             if (need) {
                 if (mine >= run_end) {
                     dead = exhausted; // otherwise: served from the next run on the next trip
@@ -329,7 +354,8 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
                             sink.path[P.method == 1 ? S : 0] = make_float2(rx, ry);
                         }
                         flat_init(m, P.planes, P.N, P.method, P.dz0, rx, ry, ta, tb);
-                        if (m.phase == PH_DONE) // N == 1: nothing to march
+                        pending = m.phase != PH_DONE;
+                        if (!pending) // N == 1: nothing to march
                             h.meta[L] = 0u;
                     }
                 }
@@ -347,24 +373,6 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
             flat_trip(m, P.planes, P.N, P.method, P.dz0, P.c, use_emis, sink);
             if (was_active && m.steps > (1u << 22))
                 m.phase = PH_DONE; // hang guard: reported as an invalid ray below
-            if (was_active && m.phase == PH_DONE) {
-                unsigned meta = (unsigned) m.seg_lo | ((unsigned) m.seg_hi << 12);
-                if (m.escaped)
-                    meta |= RTB_META_ESCAPED;
-                if (lt_0p01(fmul(m.s.z, m.s.z)) || m.steps > (1u << 22)) { // error -1 (:515-516)
-                    meta |= RTB_META_INVALID;
-                    report_failure(fail, 1, rx, ry, ra, rb);
-                } else if (h.exit_ray) {
-                    float4 e;
-                    e.x = m.pos.x;
-                    e.y = m.pos.y;
-                    e.z = fmul(atanf_fdlibm(fdiv(m.s.x, m.s.z)), 1e3f);
-                    e.w = fmul(atanf_fdlibm(fdiv(m.s.y, m.s.z)), 1e3f);
-                    h.exit_ray[L] = e;
-                }
-                h.meta[L] = meta;
-                total_steps += m.steps;
-            }
         }
     }
     if (COUNT) {
