@@ -87,6 +87,8 @@ struct PinBuf {
 struct rtb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // uploads the lineshape tables beside the running march
+    cudaEvent_t gv_ready = nullptr;
     std::string err;
     // staging
     PinBuf h_blob, h_gv;
@@ -116,8 +118,8 @@ struct rtb200_ctx {
     std::vector<cudaEvent_t> ev;
     size_t ev_used = 0;
     std::vector<std::pair<size_t, size_t>> ev_march, ev_integ; // (start, stop) indices
-    std::pair<size_t, size_t> ev_h2d{ 0, 0 }, ev_h2d_gv{ 0, 0 }, ev_d2h{ 0, 0 };
-    bool have_h2d = false, have_h2d_gv = false, have_d2h = false;
+    std::pair<size_t, size_t> ev_h2d{ 0, 0 }, ev_d2h{ 0, 0 };
+    bool have_h2d = false, have_d2h = false;
     rtb200_timings last;
     int launches = 0;
     bool count_steps = false;
@@ -147,7 +149,7 @@ void reset_timing(rtb200_ctx *ctx)
     ctx->ev_used = 0;
     ctx->ev_march.clear();
     ctx->ev_integ.clear();
-    ctx->have_h2d = ctx->have_h2d_gv = ctx->have_d2h = false;
+    ctx->have_h2d = ctx->have_d2h = false;
     ctx->launches = 0;
 }
 
@@ -164,8 +166,6 @@ void collect_timing(rtb200_ctx *ctx)
     std::memset(&t, 0, sizeof(t));
     if (ctx->have_h2d)
         t.h2d_ms = ev_ms(ctx, ctx->ev_h2d);
-    if (ctx->have_h2d_gv)
-        t.h2d_ms += ev_ms(ctx, ctx->ev_h2d_gv);
     if (ctx->have_d2h)
         t.d2h_ms = ev_ms(ctx, ctx->ev_d2h);
     for (auto &p : ctx->ev_march)
@@ -267,10 +267,13 @@ int flush_gv(rtb200_ctx *ctx, cudaStream_t st)
         return RTB200_OK;
     pack_gv(*ctx->gv_pending, ctx->h_gv.p);
     ctx->gv_pending = nullptr;
-    ctx->ev_h2d_gv.first = new_event(ctx, st);
-    RTB_CUDA(cudaMemcpyAsync(ctx->d_gv.p, ctx->h_gv.p, ctx->gv_bytes, cudaMemcpyHostToDevice, st));
-    ctx->ev_h2d_gv.second = new_event(ctx, st);
-    ctx->have_h2d_gv = true;
+    // The copy runs on its own stream next to the march; `st` only waits for its completion.
+    // (d_gv is not read by anything that is still in flight: the previous image's integration
+    // finished before its results were read back.)
+    RTB_CUDA(cudaMemcpyAsync(ctx->d_gv.p, ctx->h_gv.p, ctx->gv_bytes, cudaMemcpyHostToDevice,
+                             ctx->copy_stream));
+    RTB_CUDA(cudaEventRecord(ctx->gv_ready, ctx->copy_stream));
+    RTB_CUDA(cudaStreamWaitEvent(st, ctx->gv_ready, 0));
     return RTB200_OK;
 }
 
@@ -467,6 +470,10 @@ int rtb200_create(int device, rtb200_ctx **out)
         return fail(e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
         return fail(e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return fail(e);
+    if ((e = cudaEventCreateWithFlags(&ctx->gv_ready, cudaEventDisableTiming)) != cudaSuccess)
+        return fail(e);
     if ((e = cudaMalloc((void **) &ctx->d_fail, sizeof(FailState))) != cudaSuccess)
         return fail(e);
     if ((e = cudaMallocHost((void **) &ctx->h_fail, sizeof(FailState))) != cudaSuccess)
@@ -522,6 +529,10 @@ void rtb200_destroy(rtb200_ctx *ctx)
         cudaEventDestroy(e);
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream)
+        cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->gv_ready)
+        cudaEventDestroy(ctx->gv_ready);
     delete ctx;
 }
 
