@@ -362,17 +362,24 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
             }
             run_next = after < run_end ? after : run_end;
         }
+        const unsigned dead_mask = __ballot_sync(0xffffffffu, dead);
         if (__ballot_sync(0xffffffffu, m.phase != PH_DONE) == 0u) {
-            if (__ballot_sync(0xffffffffu, !dead) == 0u)
+            if (dead_mask == 0xffffffffu)
                 break;
             continue;
         }
-        {
+        // Inner loop: trips until enough lanes have finished for a batched refill (or the
+        // warp has run dry).  Keeping the refill code out of this loop keeps its live ranges
+        // out of the hot path.
+        for (;;) {
             // every lane takes the trip (finished lanes fall through): see flat_trip
             const bool was_active = m.phase != PH_DONE;
             flat_trip(m, P.planes, P.N, P.method, P.dz0, P.c, use_emis, sink);
             if (was_active && m.steps > (1u << 22))
                 m.phase = PH_DONE; // hang guard: reported as an invalid ray below
+            const unsigned idle = __ballot_sync(0xffffffffu, m.phase == PH_DONE);
+            if (idle == 0xffffffffu || (__popc(idle & ~dead_mask) >= RTB_REFILL_MIN))
+                break;
         }
     }
     if (COUNT) {
