@@ -1293,14 +1293,12 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
     int cur_bin = -1;
     const bool combine = K <= 32 * KS; // single pass over the bins
     auto flush_pix = [&]() {
-        if (cur_pix >= 0) {
 #pragma unroll
-            for (int q = 0; q < KS; q++) {
-                const int k = lane + 32 * q;
-                if (k < K)
-                    atomicAdd(&o.image[(size_t) K * (size_t) cur_pix + k], acc[q]);
-                acc[q] = 0.0;
-            }
+        for (int q = 0; q < KS; q++) {
+            const int k = lane + 32 * q;
+            if (cur_pix >= 0 && k < K)
+                atomicAdd(&o.image[(size_t) K * (size_t) cur_pix + k], acc[q]);
+            acc[q] = 0.0; // also after a run of rays that left the image (cur_pix < 0): dropped
         }
         cur_pix = -1;
     };
