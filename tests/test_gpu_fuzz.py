@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 def _case(small, seed):
     rng = np.random.default_rng(seed)
     p = small
-    K = int(rng.choice([17, 32, 52, 64, 77]))
+    K = int(rng.choice([17, 32, 52, 64, 77, 130, 200]))
     if K != p.euv_beam.nv:
         p = synth.spectral(p, K)
     euv = synth.scale_beam(p.euv_beam, float(rng.choice([0.6, 0.8, 1.0, 1.25])))
@@ -58,6 +58,15 @@ def test_random_configuration(seed, ase_small, oracle, ctx):
         assert rel_l2(img, oi["image"]) <= 1e-10 and max_rel(img, oi["image"]) <= 1e-9, seed
     if np.linalg.norm(oi["I_ang"]) > 0:
         assert rel_l2(ang, oi["I_ang"]) <= 1e-10 and max_rel(ang, oi["I_ang"]) <= 1e-9, seed
+    # the same rays as an explicit list (RayTraceImage<Backend>Loop), accumulated on top of a
+    # non-zero image: scatter binning instead of pixel ownership
+    base_img = np.full_like(oi["image"], 0.25 * np.abs(oi["image"]).max())
+    base_ang = np.zeros_like(oi["I_ang"])
+    gi, ga = base_img.copy(), base_ang.copy()
+    wi, wa = base_img.copy(), base_ang.copy()
+    ctx.trace_rays(p, rays, 1, 0.5, gi, ga)
+    oracle.trace_rays(p, rays, 1, 0.5, wi, wa)
+    assert rel_l2(gi, wi) <= 1e-10 and rel_l2(ga, wa + 1e-300) <= 1e-10, seed
 
 
 @pytest.mark.parametrize("seed", range(10))
@@ -85,3 +94,15 @@ def test_random_seeded_configuration(seed, seed_small, oracle, ctx):
     assert np.linalg.norm(oi["image"]) > 0
     assert rel_l2(img, oi["image"]) <= 1e-10 and max_rel(img, oi["image"]) <= 1e-9, seed
     assert rel_l2(ang, oi["I_ang"]) <= 1e-10 and max_rel(ang, oi["I_ang"]) <= 1e-9, seed
+    # explicit ray lists through the same kernels: forward (seed at the entry point, binned by the
+    # exit ray) and backward (seed at the exit point, binned by the ray itself)
+    rays = p.rays()[:: 7]
+    for method in (2, 1):
+        gi, ga = np.zeros_like(img), np.zeros_like(ang)
+        wi, wa = np.zeros_like(img), np.zeros_like(ang)
+        ctx.trace_rays(p, rays, method, 2.0, gi, ga)
+        oracle.trace_rays(p, rays, method, 2.0, wi, wa)
+        if np.linalg.norm(wi) > 0:
+            assert rel_l2(gi, wi) <= 1e-10 and max_rel(gi, wi) <= 1e-9, (seed, method)
+        if np.linalg.norm(wa) > 0:
+            assert rel_l2(ga, wa) <= 1e-10 and max_rel(ga, wa) <= 1e-9, (seed, method)
