@@ -106,3 +106,62 @@ def test_random_seeded_configuration(seed, seed_small, oracle, ctx):
             assert rel_l2(gi, wi) <= 1e-10 and max_rel(gi, wi) <= 1e-9, (seed, method)
         if np.linalg.norm(wa) > 0:
             assert rel_l2(ga, wa) <= 1e-10 and max_rel(ga, wa) <= 1e-9, (seed, method)
+
+
+def _unmirrored(p):
+    """The same plasma with the y < 0 half spelled out (gain planes and beam grid symmetric about
+    y = 0) instead of mirrored by |y|: the abs_y = 0 branches of the march and of the binning."""
+    def full(g):
+        assert g.y[0] == 0.0
+        y = np.concatenate([-g.y[:0:-1], g.y])
+        m = lambda a: None if a is None else np.concatenate([a[:0:-1], a], axis=0)  # noqa: E731
+        return abi.Gain(g.x, y, m(g.n), m(g.g0), m(g.E0), m(g.gv), m(g.gv0))
+    e = p.euv_beam
+    euv = abi.BeamGrid(e.x, np.concatenate([-e.y[::-1], e.y]), e.a, e.b, e.dx, e.dy, e.da, e.db,
+                       dv=e.dv, dz=e.dz, extra={})
+    return abi.Problem(euv, [full(g) for g in p.gain], None, None, p.N_start, p.N_parallel)
+
+
+def test_unmirrored_plasma(ase_small, oracle, ctx):
+    p = _unmirrored(ase_small[0])
+    assert p.gain[1].y[0] < 0 and p.euv_beam.y[0] < 0
+    p.N_start, p.N_parallel = 4, 17
+    rays = p.rays()[::13]
+    g, o = ctx.calc_rays(p, rays), oracle.calc_rays(p, rays)
+    assert np.array_equal(g["error"], o["error"])
+    for f in ("gvl", "evl"):
+        assert np.array_equal(g[f].view(np.uint32), o[f].view(np.uint32)), f
+    img, ang = ctx.create_image(p)
+    oi = oracle.create_image(p)
+    assert np.linalg.norm(oi["image"]) > 0
+    assert rel_l2(img, oi["image"]) <= 1e-10 and max_rel(img, oi["image"]) <= 1e-9
+    assert rel_l2(ang, oi["I_ang"]) <= 1e-10 and max_rel(ang, oi["I_ang"]) <= 1e-9
+
+
+def test_seed_narrower_than_the_beam(seed_small, oracle, ctx, monkeypatch):
+    """A seed profile that covers only part of the seed beam in x and in a: rays outside it carry
+    no seed (calc_seed_inline's range test; NaN entries of the per-index factor tables), and a
+    hand-off arena of 2 MB so that the image is assembled from many chunks."""
+    p0 = seed_small[0]
+    sd = p0.seed
+    x0 = np.linspace(0.0022, 0.0051, 97)
+    a0 = np.linspace(-1.1, 0.9, 61)
+    x = [x0, sd.x[1], a0, sd.x[3], sd.x[4]]
+    f = [np.interp(x0, sd.x[0], sd.f[0]), sd.f[1], np.interp(a0, sd.x[2], sd.f[2]), sd.f[3], sd.f[4]]
+    p = abi.Problem(p0.euv_beam, p0.gain, p0.seed_beam, abi.SeedProfile(x, f, sd.f0), 11, 173)
+    oi = oracle.create_image(p)
+    assert np.linalg.norm(oi["image"]) > 0
+    from raytrace_miniapp_b200 import lib
+    monkeypatch.setenv("RTB200_HANDOFF_MB", "2")
+    small_arena = lib.Context(0)
+    for c in (ctx, small_arena):
+        img, ang = c.create_image(p)
+        assert rel_l2(img, oi["image"]) <= 1e-10 and max_rel(img, oi["image"]) <= 1e-9
+        assert rel_l2(ang, oi["I_ang"]) <= 1e-10 and max_rel(ang, oi["I_ang"]) <= 1e-9
+    small_arena.close()
+    g = ctx.calc_rays(p, p.rays()[::5])
+    o = oracle.calc_rays(p, p.rays()[::5])
+    assert (np.abs(o["Iv"]).max(axis=1) == 0).sum() > 100  # rays without seed exist ...
+    assert (np.abs(o["Iv"]).max(axis=1) > 0).sum() > 100  # ... and rays with seed
+    sc = np.abs(o["Iv"]).max(axis=1, keepdims=True) + 1e-300
+    assert np.max(np.abs(g["Iv"] - o["Iv"]) / sc) < 1e-12
