@@ -700,17 +700,15 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
         float gA[KS], gB[KS];
         fetch(0, eA, gA);
         for (int j = 0;; j += 2) {
-            const bool haveB = j + 1 < cnt;
-            if (haveB)
-                fetch(j + 1, eB, gB);
+            // the prefetch index is clamped instead of guarded: past the end it re-reads the last
+            // record (unused), which costs less than a branch and a reconvergence point
+            fetch(min(j + 1, cnt - 1), eB, gB);
             update(__uint_as_float(eA.x), __uint_as_float(eA.y), gA);
-            if (!haveB)
+            if (j + 1 >= cnt)
                 break;
-            const bool haveA = j + 2 < cnt;
-            if (haveA)
-                fetch(j + 2, eA, gA);
+            fetch(min(j + 2, cnt - 1), eA, gA);
             update(__uint_as_float(eB.x), __uint_as_float(eB.y), gB);
-            if (!haveA)
+            if (j + 2 >= cnt)
                 break;
         }
     }
