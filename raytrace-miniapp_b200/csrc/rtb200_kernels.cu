@@ -646,12 +646,10 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
         auto update = [&](float gvl, float evl, const float (&g)[KS]) {
             if (gvl == 0.0f && evl == 0.0f)
                 return; // gl = el = 0: the update is the identity
-            // One warp-wide OR gathers every branch decision of the record: bit 2q = "some lane
-            // of slot q takes the Taylor branch", bit 2q+1 = "some lane takes the exp branch",
-            // bit 31 = "some |gl| >= 700, inf or NaN" (library semantics).
+            // Branch decisions by warp votes: their results are uniform predicates, so the
+            // dispatch below costs a branch each and nothing else.
             float glf[KS], elf[KS];
             bool small[KS];
-            unsigned flags = 0u;
             float ag_sum = 0.0f; // one range test for all slots: sum of |gl| (NaN and inf propagate)
 #pragma unroll
             for (int q = 0; q < KS; q++) {
@@ -659,12 +657,9 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
                 elf[q] = __fmul_rn(evl, g[q]);
                 const float ag = fabsf(glf[q]);
                 small[q] = ag < 1e-3f; // == (fabs((double) glf) < 1e-3)
-                flags |= (small[q] ? 1u : 2u) << (2 * q);
                 ag_sum += ag;
             }
-            flags |= !(ag_sum < 700.0f) ? 0x80000000u : 0u; // conservative: library path is always valid
-            flags = __reduce_or_sync(0xffffffffu, flags);
-            if (flags & 0x80000000u) {
+            if (__any_sync(0xffffffffu, !(ag_sum < 700.0f))) { // conservative: library path is always valid
 #pragma unroll
                 for (int q = 0; q < KS; q++)
                     Iv[q] = ase_update_library(Iv[q], (double) glf[q], (double) elf[q]);
@@ -673,12 +668,11 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
 #pragma unroll
             for (int q = 0; q < KS; q++) {
                 const double gl = (double) glf[q], el = (double) elf[q];
-                const unsigned f = (flags >> (2 * q)) & 3u; // warp-uniform
                 // three straight-line variants: the common one (every lane of the slot on the
                 // exp branch) carries no select and no dead Taylor result
-                if (__builtin_expect(f == 2u, 1)) {
+                if (__builtin_expect(!__any_sync(0xffffffffu, small[q]), 1)) {
                     Iv[q] = ase_update_large(Iv[q], gl, el, rcp_approx(glf[q]), KC);
-                } else if (__builtin_expect(f == 1u, 0)) {
+                } else if (__builtin_expect(__all_sync(0xffffffffu, small[q]), 0)) {
                     Iv[q] = ase_update_small(Iv[q], gl, el, KC);
                 } else {
                     const double a = ase_update_small(Iv[q], gl, el, KC);
