@@ -277,9 +277,11 @@ def run_gpu(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         traffic = None
+        executed_per_update = None
         try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["integrate_ase_owner_kernel"]
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            executed_per_update = tj.get("fp64_instr_per_update_executed")
         except Exception:
             pass
         launches_integ = max(1, launches_per_step // 2) * K
@@ -312,9 +314,19 @@ def run_gpu(args):
                 "frac": achieved_tflops / peak_tflops, "traffic": traffic,
                 "traffic_note": "dram read+write bytes per launch (ncu, profiles/r01_traffic.json): the "
                                 "march->integrate hand-off records, not re-reads of the inputs",
-                "convention": "%d FP64 instr per frequency update (SURVEY.md 8d) x 2 flop; peak = "
-                              "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has "
-                              "no FP64 entry)" % FP64_INSTR_PER_UPDATE,
+                "convention": "%d FP64 instr per frequency update (SURVEY.md 8d: the reference formula "
+                              "with library exp and divide) x 2 flop; peak = DFMA micro-benchmark measured "
+                              "in this run (MEASURED_PEAKS.json has no FP64 entry).  The kernel's own exp / "
+                              "reciprocal need fewer FP64 instructions than that, so this figure can pass "
+                              "1.0; `executed` is the FP64 work the kernel really issues" % FP64_INSTR_PER_UPDATE,
+                "executed": None if executed_per_update is None else {
+                    "fp64_instr_per_update": executed_per_update,
+                    "achieved": achieved_tflops * executed_per_update / FP64_INSTR_PER_UPDATE,
+                    "frac": achieved_tflops * executed_per_update / FP64_INSTR_PER_UPDATE / peak_tflops,
+                    "unit": "TFLOP/s",
+                    "note": "per-update count from the committed ncu capture (profiles/r01_traffic.json); "
+                            "the kernel is bound by instruction issue (72.7% of the issue slots), the "
+                            "FP64 pipe is 45.7% busy"},
                 "avg_launch_ms": integ_ms / launches_integ,
                 "hbm": {"achieved": alg_bytes * K / integ_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": alg_bytes * K / integ_s / 1e9 / hbm_peak,
