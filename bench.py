@@ -284,6 +284,11 @@ def run_gpu(args):
             executed_per_update = tj.get("fp64_instr_per_update_executed")
         except Exception:
             pass
+        march_prof = {}
+        try:
+            march_prof = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["march_flat_kernel"]
+        except Exception:
+            pass
         launches_integ = max(1, launches_per_step // 2) * K
         integ_s = integ_ms * 1e-3
         upd_local = W_upd / world  # per rank (weak: identical tiles)
@@ -321,6 +326,20 @@ def run_gpu(args):
             "hbm": {"achieved": alg_bytes * K / integ_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": alg_bytes * K / integ_s / 1e9 / hbm_peak,
                     "note": "algorithmic bytes only; the path is FP64/issue-bound, not HBM-bound"}}
+        # The march (the larger half of the step) has no pipe roofline: scalar FP32 / mixed FP64
+        # per ray with data-dependent trip counts.  Its bound is instruction issue x SIMT
+        # efficiency; both factors from the committed ncu capture, the rate from this run.
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        if march_prof.get("warp_instr_per_launch") and sms and args.scaling == "weak":
+            issue_peak = sms * 4 * (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
+            rate = march_prof["warp_instr_per_launch"] * K / (march_ms * 1e-3)
+            roofline["march_kernel"] = {
+                "kernel": "march_flat_kernel", "bound": "issue", "unit": "warp-instr/s",
+                "achieved": rate, "peak": issue_peak, "frac": rate / issue_peak,
+                "simt_efficiency": march_prof.get("active_threads_per_instr", 0) / 32.0,
+                "avg_launch_ms": march_ms / launches_integ,
+                "note": "peak = SMs x 4 schedulers x SM clock; instructions per launch from ncu "
+                        "(profiles/r01_traffic.json, N=1 workload; per GPU the same in weak scaling)"}
         line = {
             "metric": "ray_segments_per_s", "value": value, "unit": "ray-segments/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_per_step,
