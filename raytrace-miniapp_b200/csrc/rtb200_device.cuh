@@ -54,6 +54,10 @@ struct DevProblem {
     // owner tables for method 1 (ray2 = ray): getIndex of the source coordinate, -1 = outside
     const int *pixI, *pixJ, *binA, *binB;
     const double *dv2; // 2.0*dv[k]
+    // largest |gv| of all planes as float bits (NaN sorts above everything); 0x7fffffff = not
+    // known.  Lets the ASE integration skip its per-record exp-range test for a whole ray when
+    // max|gvl| * max|gv| < 700 (rtb200_kernels.cu, integrate_ray_ase_fast).
+    unsigned gv_absmax_bits;
     // --- separable seed, tabulated per source index (method 2): factor, or NaN when the
     //     coordinate is outside the seed grid (calc_seed_inline's range test, :235-237)
     const double *seed_fx, *seed_fy, *seed_fa, *seed_fb, *seed_fv;

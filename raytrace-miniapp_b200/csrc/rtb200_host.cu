@@ -265,7 +265,7 @@ int flush_gv(rtb200_ctx *ctx, cudaStream_t st)
 {
     if (!ctx->gv_pending)
         return RTB200_OK;
-    pack_gv(*ctx->gv_pending, ctx->h_gv.p);
+    ctx->prob.gv_absmax_bits = pack_gv(*ctx->gv_pending, ctx->h_gv.p);
     ctx->gv_pending = nullptr;
     // The copy runs on its own stream next to the march; `st` only waits for its completion.
     // (d_gv is not read by anything that is still in flight: the previous image's integration

@@ -632,16 +632,24 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
         // shared-memory slab: one 16-byte broadcast read per record replaces three shuffles,
         // the plane look-up and the 64-bit address arithmetic.
         __syncwarp();
+        unsigned gvl_abs = 0u;
         if (lane < cnt) {
             const int4 rv = __ldg(reinterpret_cast<const int4 *>(&seg[c0 + lane]));
             const float *row = s_gv[(c0 + lane) / RTB_N_SUB + 1] + (size_t) rv.z * K;
             const unsigned long long ra = reinterpret_cast<unsigned long long>(row);
+            gvl_abs = (unsigned) rv.x & 0x7fffffffu;
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slab + 16u * (unsigned) lane),
                          "r"((unsigned) rv.x), "r"((unsigned) rv.y), "r"((unsigned) ra),
                          "r"((unsigned) (ra >> 32))
                          : "memory");
         }
         __syncwarp();
+        // exp-range test of the records (|gl| >= 700, inf, NaN -> library exp): needed for none
+        // of these records if max|gvl| * max|gv| stays below 700 (bit patterns order like the
+        // magnitudes, NaN above everything; the comparison is false for NaN)
+        const float gvl_max = __uint_as_float(__reduce_max_sync(0xffffffffu, gvl_abs));
+        const bool range_test =
+            !(__fmul_rn(__fmul_rn(gvl_max, __uint_as_float(P.gv_absmax_bits)), 1.000001f) < 700.0f);
         // The update of one record; `g` are the lineshape values of this lane's bins.
         auto update = [&](float gvl, float evl, const float (&g)[KS]) {
             if (gvl == 0.0f && evl == 0.0f)
@@ -650,16 +658,21 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
             // dispatch below costs a branch each and nothing else.
             float glf[KS], elf[KS];
             bool small[KS];
-            float ag_sum = 0.0f; // one range test for all slots: sum of |gl| (NaN and inf propagate)
 #pragma unroll
             for (int q = 0; q < KS; q++) {
                 glf[q] = __fmul_rn(gvl, g[q]);
                 elf[q] = __fmul_rn(evl, g[q]);
-                const float ag = fabsf(glf[q]);
-                small[q] = ag < 1e-3f; // == (fabs((double) glf) < 1e-3)
-                ag_sum += ag;
+                small[q] = fabsf(glf[q]) < 1e-3f; // == (fabs((double) glf) < 1e-3)
             }
-            if (__any_sync(0xffffffffu, !(ag_sum < 700.0f))) { // conservative: library path is always valid
+            bool out_of_range = false;
+            if (range_test) { // warp-uniform; one test for all slots: sum of |gl| (NaN, inf propagate)
+                float ag_sum = 0.0f;
+#pragma unroll
+                for (int q = 0; q < KS; q++)
+                    ag_sum += fabsf(glf[q]);
+                out_of_range = __any_sync(0xffffffffu, !(ag_sum < 700.0f));
+            }
+            if (out_of_range) { // conservative: the library path is always valid
 #pragma unroll
                 for (int q = 0; q < KS; q++)
                     Iv[q] = ase_update_library(Iv[q], (double) glf[q], (double) elf[q]);

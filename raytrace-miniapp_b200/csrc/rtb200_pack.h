@@ -201,6 +201,17 @@ struct GvBlob {
     size_t bytes;
 };
 
+// max over |v| as float bit patterns (sign cleared; NaN > inf > every finite value)
+inline unsigned abs_max_bits(const float *v, size_t n, unsigned m = 0u)
+{
+    const uint32_t *b = reinterpret_cast<const uint32_t *>(v);
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t a = b[i] & 0x7fffffffu;
+        m = a > m ? a : m;
+    }
+    return m;
+}
+
 // Packs `p` into the blob.  Returns the number of bytes used; fills `out` (pointers relative
 // to dev_base).  explicit_rays: the ray list comes separately (rtb200_trace_rays), so only the
 // planes, the destination grid and dv are packed and method/scale are given by the caller.
@@ -228,6 +239,7 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
         std::memcpy(kfp_g, kfp, sizeof(kfp));
 
     // ---- gain planes ------------------------------------------------------------------------
+    unsigned gv_absmax = 0u;
     DevPlane *planes = blob.alloc<DevPlane>((size_t) N, &out.planes);
     for (int ii = 0; ii < N; ii++) {
         const rtb200_gain_plane &g = p.gain[ii];
@@ -278,8 +290,12 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
                 node[q].g0 = g.g0[q];
                 node[q].E0 = g.E0 ? g.E0[q] : 0.0f;
             }
-            if (gv && (!gvb || gvb->copy))
+            if (gv && (!gvb || gvb->copy)) {
                 std::memcpy(gv, g.gv, sizeof(float) * nn * (size_t) K);
+                gv_absmax = abs_max_bits(g.gv, nn * (size_t) K, gv_absmax);
+            } else {
+                gv_absmax = 0x7fffffffu; // tables filled later: pack_gv() returns the value
+            }
             P.Nx = g.Nx;
             P.Ny = g.Ny;
             P.range[0] = (float) g.x[0]; // :445-453
@@ -302,6 +318,8 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
             planes[ii] = P;
         }
     }
+
+    out.gv_absmax_bits = fill ? gv_absmax : 0x7fffffffu;
 
     // ---- destination grid (euv_beam) --------------------------------------------------------
     out.nx = e.nx;
@@ -424,17 +442,21 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
 }
 
 // Fills a GvBlob that pack_problem laid out with copy == false (same allocation sequence).
-inline void pack_gv(const rtb200_problem &p, char *host)
+// Returns DevProblem::gv_absmax_bits.
+inline unsigned pack_gv(const rtb200_problem &p, char *host)
 {
     Blob gv_blob(host, host);
     const int K = p.euv_beam->nv;
+    unsigned m = 0u;
     for (int ii = 0; ii < p.N; ii++) {
         const rtb200_gain_plane &g = p.gain[ii];
         const size_t n = (size_t) g.Nx * g.Ny * (size_t) K;
         const float *unused;
         float *gv = gv_blob.alloc<float>(n, &unused);
         std::memcpy(gv, g.gv, sizeof(float) * n);
+        m = abs_max_bits(g.gv, n, m);
     }
+    return m;
 }
 
 } // namespace rtb
