@@ -314,8 +314,8 @@ def run_gpu(args):
             "convention": "%.2f FP64 instr issued per frequency update (ncu count of this kernel, "
                           "profiles/r01_traffic.json) x 2 flop x updates / kernel time; peak = DFMA "
                           "micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 "
-                          "entry).  The kernel is bound by instruction issue (72.7%% of the issue "
-                          "slots busy, FP64 pipe 45.7%%)" % per_upd,
+                          "entry).  The kernel is bound by instruction issue (72%% of the issue "
+                          "slots busy, FP64 pipe 47%%)" % per_upd,
             "survey_convention": {
                 "fp64_instr_per_update": FP64_INSTR_PER_UPDATE, "achieved": achieved_tflops,
                 "frac": achieved_tflops / peak_tflops, "unit": "TFLOP/s",
