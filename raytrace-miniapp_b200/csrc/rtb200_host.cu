@@ -211,7 +211,8 @@ int validate(rtb200_ctx *ctx, const rtb200_problem *p, unsigned flags)
     }
     {
         const rtb200_beam &g = p->seed ? *p->seed_beam : e;
-        if ((long long) g.nx * g.ny >= (1LL << 31) || (long long) g.na * g.nb >= (1LL << 31)) {
+        if ((long long) g.nx * g.ny >= (1LL << 31) || (long long) g.na * g.nb >= (1LL << 31) ||
+            (long long) e.nx * e.ny >= (1LL << 31) || (long long) e.na * e.nb >= (1LL << 31)) {
             ctx->err = "more than 2^31 source pixels or angles per pixel";
             return RTB200_ERR_LIMITS;
         }

@@ -1294,7 +1294,7 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
     for (int q = 0; q < KS; q++)
         acc[q] = 0.0;
     double acc_w = 0.0;
-    long long cur_pix = -1;
+    int cur_pix = -1; // destination pixels fit 32 bits (validated on the host)
     int cur_bin = -1;
     const bool combine = K <= 32 * KS; // single pass over the bins
     auto flush_pix = [&]() {
@@ -1343,7 +1343,7 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
     // and the destination pixel / angular bin.  Evaluated by ONE lane per slot, 32 slots at a
     // time, and handed to the warp by shuffles (it used to be repeated by all 32 lanes of the
     // warp for every ray: ~250 of ~800 instructions per ray).
-    auto prologue = [&](long long slot, unsigned meta, double &f, long long &pix, int &bin) {
+    auto prologue = [&](long long slot, unsigned meta, double &f, int &pix, int &bin) {
         float rx, ry, ra, rb;
         int pi, pj, ka, m;
         slot_ray(slot, rx, ry, ra, rb, pi, pj, ka, m);
@@ -1384,25 +1384,18 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
             const int i3 = dev_get_index(P.na, P.ea, P.eda, (double) ba);
             const int i4 = dev_get_index(P.nb, P.eb, P.edb, (double) bb);
             if (o.image && i1 >= 0 && i2 >= 0)
-                pix = (long long) i1 + (long long) i2 * P.nx;
+                pix = i1 + i2 * P.nx;
             if (i3 >= 0 && i4 >= 0)
                 bin = i3 + i4 * P.na;
         }
     };
-    // seed spectrum of this lane's bins (single pass over the bins)
-    double fv[KS];
-#pragma unroll
-    for (int q = 0; q < KS; q++) {
-        const int k = lane + 32 * q;
-        fv[q] = (combine && P.seed_fv && k < K) ? __ldg(&P.seed_fv[k]) : 0.0;
-    }
     const long long n_runs = (n_slots + RUN - 1) / RUN;
     for (long long run = warp_id; run < n_runs; run += n_warps) {
     const long long slot_end = (run + 1) * RUN < n_slots ? (run + 1) * RUN : n_slots;
     for (long long base = run * RUN; base < slot_end; base += 32) {
     unsigned meta_l = RTB_META_INACTIVE;
     double f_l = 0.0;
-    long long pix_l = -1;
+    int pix_l = -1;
     int bin_l = -1;
     if (base + lane < slot_end) {
         meta_l = __ldg(&h.meta[base + lane]);
@@ -1417,7 +1410,7 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
         if (meta & RTB_META_INACTIVE)
             continue;
         const double f = __shfl_sync(0xffffffffu, f_l, j);
-        const long long pix = __shfl_sync(0xffffffffu, pix_l, j);
+        const int pix = __shfl_sync(0xffffffffu, pix_l, j);
         const int bin = __shfl_sync(0xffffffffu, bin_l, j);
         const bool invalid = (meta & RTB_META_INVALID) != 0;
         int code = invalid ? 1 : 0;
@@ -1428,10 +1421,9 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
 #pragma unroll
             for (int q = 0; q < KS; q++) {
                 const int k = kbase + lane + 32 * q;
-                if (combine)
-                    Iv[q] = f != 0.0 ? __dmul_rn(f, fv[q]) : 0.0; // fv = 0 for k >= K
-                else
-                    Iv[q] = (f != 0.0 && k < K) ? __dmul_rn(f, __ldg(&P.seed_fv[k])) : 0.0;
+                // (the seed spectrum is re-read per ray: holding it in registers costs more in
+                // spills than the three L1 hits, measured 5.46 vs 5.19 ms on seed_small)
+                Iv[q] = (f != 0.0 && k < K) ? __dmul_rn(f, __ldg(&P.seed_fv[k])) : 0.0;
             }
             if (!invalid) {
                 const int cc = gain_only
