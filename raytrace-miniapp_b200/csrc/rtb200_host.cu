@@ -733,6 +733,12 @@ int launch_list(rtb200_ctx *ctx, size_t n_rays, const Outputs &out_all, bool kee
     long long per_chunk = keep_handoff ? (long long) n_rays
                                        : std::max<long long>(1, (long long) (ctx->handoff_bytes / per_slot));
     per_chunk = std::min<long long>(per_chunk, (long long) n_rays);
+    const long long max_slots = (1LL << 31) - 64; // the kernels count the slots of a chunk in 32 bits
+    if (keep_handoff && per_chunk > max_slots) {
+        ctx->err = "more than 2^31 rays in one call that keeps the per-ray intermediates";
+        return RTB200_ERR_LIMITS;
+    }
+    per_chunk = std::min(per_chunk, max_slots);
     int rc = ensure_handoff(ctx, per_chunk, true);
     if (rc)
         return rc;

@@ -1277,9 +1277,10 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
     const int lane = threadIdx.x & 31;
     const unsigned slab =
         __shfl_sync(0xffffffffu, (unsigned) __cvta_generic_to_shared(&rec_slab[threadIdx.x >> 5][0]), 0);
-    const long long warp_id = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long n_warps = ((long long) gridDim.x * blockDim.x) >> 5;
-    const long long n_slots = LIST ? (c.ray1 - c.ray0) : (c.pix1 - c.pix0) * P.ab_max;
+    // slot counts of one chunk fit 32 bits (the host sizes chunks that way): 32-bit loop counters
+    const int warp_id = (int) ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int n_warps = (int) ((gridDim.x * blockDim.x) >> 5);
+    const int n_slots = (int) (LIST ? (c.ray1 - c.ray0) : (c.pix1 - c.pix0) * P.ab_max);
     const int S = (P.N - 1) * RTB_N_SUB;
     const int K = P.K;
     // Each warp takes RUN consecutive ray slots at a time.  Consecutive rays (b fastest, then a)
@@ -1389,10 +1390,10 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
                 bin = i3 + i4 * P.na;
         }
     };
-    const long long n_runs = (n_slots + RUN - 1) / RUN;
-    for (long long run = warp_id; run < n_runs; run += n_warps) {
-    const long long slot_end = (run + 1) * RUN < n_slots ? (run + 1) * RUN : n_slots;
-    for (long long base = run * RUN; base < slot_end; base += 32) {
+    const int n_runs = (n_slots + RUN - 1) / RUN;
+    for (int run = warp_id; run < n_runs; run += n_warps) {
+    const int slot_end = min((run + 1) * RUN, n_slots);
+    for (int base = run * RUN; base < slot_end; base += 32) {
     unsigned meta_l = RTB_META_INACTIVE;
     double f_l = 0.0;
     int pix_l = -1;
@@ -1403,9 +1404,9 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
             prologue(base + lane, meta_l, f_l, pix_l, bin_l);
     }
     __syncwarp();
-    const int n_here = (int) (slot_end - base < 32 ? slot_end - base : 32);
+    const int n_here = min(slot_end - base, 32);
     for (int j = 0; j < n_here; j++) {
-        const long long slot = base + j;
+        const long long slot = base + j; // 64-bit where it scales addresses
         const unsigned meta = __shfl_sync(0xffffffffu, meta_l, j);
         if (meta & RTB_META_INACTIVE)
             continue;
