@@ -1259,7 +1259,7 @@ __device__ double dev_calc_seed(const DevProblem &P, double x, double y, double 
 // One warp per ray slot; K is covered in passes of 32*KS bins (one pass for K <= 128).  Handles both integration modes,
 // both ray sources, scatter binning and the per-ray dumps.
 #ifndef RTB_SCATTER_MINBLOCKS
-#define RTB_SCATTER_MINBLOCKS 3
+#define RTB_SCATTER_MINBLOCKS 4
 #endif
 template <bool LIST, int KS>
 __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
