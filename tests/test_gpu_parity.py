@@ -302,3 +302,26 @@ def test_vacuum_planes_and_empty_inputs(ase_small, oracle, ctx):
     ang0 = np.zeros_like(ang)
     ctx.trace_rays(p, none, p.method, 1.0, img0.ravel(), ang0.ravel())
     assert not img0.any() and not ang0.any()
+
+
+def test_launch_after_create_image_uses_the_staged_problem(ase_small, ctx):
+    """create_image stages the problem in two uploads (the lineshape tables follow while the
+    march runs); a launch on the same context afterwards must find the staging complete, and a
+    second create_image with other gains must not see the tables of the first."""
+    import torch
+    p, _ = ase_small
+    e = p.euv_beam
+    img, ang = ctx.create_image(p)
+    dev_i = torch.zeros(e.nx * e.ny * e.nv, dtype=torch.float64, device="cuda")
+    dev_a = torch.zeros(e.na * e.nb, dtype=torch.float64, device="cuda")
+    ctx.launch(0, ctx.staged_pixels, dev_i, dev_a)
+    ctx.sync()
+    assert np.array_equal(dev_i.cpu().numpy(), img)
+    assert rel_l2(dev_a.cpu().numpy(), ang) < 1e-14
+    planes = [abi.Gain(g.x, g.y, g.n, g.g0, g.E0, g.gv * np.float32(0.5), g.gv0) for g in p.gain]
+    q = abi.Problem(p.euv_beam, planes, None, None, p.N_start, p.N_parallel)
+    img2, _ = ctx.create_image(q)
+    fresh = type(ctx)(0)
+    img3, _ = fresh.create_image(q)
+    fresh.close()
+    assert np.array_equal(img2, img3) and not np.array_equal(img2, img)
