@@ -25,7 +25,7 @@ struct Cursor {
     {
         T v;
         std::memset(&v, 0, sizeof(T));
-        if (pos + sizeof(T) > n) {
+        if (sizeof(T) > n - pos) { // (pos <= n always; no sum that could wrap)
             ok = false;
             return v;
         }
@@ -35,7 +35,7 @@ struct Cursor {
     }
     const unsigned char *bytes(size_t len)
     {
-        if (pos + len > n) {
+        if (len > n - pos) {
             ok = false;
             return nullptr;
         }
@@ -46,7 +46,7 @@ struct Cursor {
     // load_byte_header (src/RayTraceStructures.cpp:118-138): skip the header when present.
     int header_type()
     {
-        if (pos < n && p[pos] == 237 && pos + 16 <= n) {
+        if (pos < n && p[pos] == 237 && n - pos >= 16) {
             const int type = p[pos + 4];
             if (p[pos + 1] != 4 || p[pos + 2] != 8)
                 ok = false;
@@ -72,6 +72,10 @@ struct Owned {
     template <class T>
     T *copy(Cursor &c, size_t count)
     {
+        if (count > (c.n - c.pos) / sizeof(T)) { // also keeps count * sizeof(T) from wrapping
+            c.ok = false;
+            return nullptr;
+        }
         const unsigned char *src = c.bytes(count * sizeof(T));
         if (!src)
             return nullptr;
@@ -112,7 +116,7 @@ bool parse_euv(Owned &o, const unsigned char *b, size_t n)
     c.take<double>(); // v0
     e.x = o.copy<double>(c, e.nx);
     e.y = o.copy<double>(c, e.ny);
-    c.bytes(sizeof(double) * (size_t) nz); // z
+    c.bytes(sizeof(double) * (size_t) nz); // z (nz < 2^31: no wrap)
     e.a = o.copy<double>(c, e.na);
     e.b = o.copy<double>(c, e.nb);
     c.bytes(sizeof(double) * (size_t) e.nv); // v
@@ -155,14 +159,16 @@ bool parse_gain(Owned &o, rtb200_gain_plane &g, const unsigned char *b, size_t n
     g.Nv = c.take<int32_t>();
     if (!c.ok || g.Nx < 1 || g.Ny < 1 || g.Nv < 1)
         return false;
-    const size_t nn = (size_t) g.Nx * g.Ny;
+    const size_t nn = (size_t) g.Nx * g.Ny; // < 2^62
+    if (nn > n / sizeof(float) || (size_t) g.Nv > n / sizeof(float) / nn)
+        return false; // nn * Nv floats cannot be in this stream (and the product could wrap)
     g.x = o.copy<double>(c, g.Nx);
     g.y = o.copy<double>(c, g.Ny);
     g.n = o.copy<double>(c, nn);
     g.g0 = o.copy<float>(c, nn);
     g.E0 = o.copy<float>(c, nn);
     g.gv = o.copy<float>(c, nn * (size_t) g.Nv);
-    c.bytes(sizeof(float) * nn); // gv0: off the path
+    c.bytes(sizeof(float) * nn); // gv0: off the path (nn <= n / 4 was checked above)
     return c.ok && c.pos == n;
 }
 
@@ -197,6 +203,7 @@ int rtb200_parse_dat(const void *bytes, size_t n_bytes, rtb200_problem **problem
     Owned *o = new (std::nothrow) Owned;
     if (!o)
         return RTB200_ERR_ARG;
+    try { // nothing may propagate through the C boundary (std::bad_alloc from a hostile count)
     std::memset(&o->p, 0, sizeof(o->p));
     Cursor c(bytes, n_bytes);
     bool ok = true;
@@ -204,7 +211,7 @@ int rtb200_parse_dat(const void *bytes, size_t n_bytes, rtb200_problem **problem
     o->p.N_start = c.take<int32_t>();
     o->p.N_parallel = c.take<int32_t>();
     c.take<double>(); // dz (duplicated inside euv_beam)
-    ok = ok && c.ok && o->p.N >= 1 && o->p.N < (1 << 20);
+    ok = ok && c.ok && o->p.N >= 1 && (size_t) o->p.N <= n_bytes / 16; // a plane takes > 16 bytes
     if (ok) {
         const uint32_t nb = c.take<uint32_t>();
         const unsigned char *b = c.bytes(nb);
@@ -241,8 +248,12 @@ int rtb200_parse_dat(const void *bytes, size_t n_bytes, rtb200_problem **problem
                 o->p.seed = &o->seed;
         }
     }
-    if (ok && c.take<unsigned char>())
-        o->golden_image = o->copy<double>(c, (size_t) o->euv.nx * o->euv.ny * o->euv.nv);
+    if (ok && c.take<unsigned char>()) {
+        const size_t nxy = (size_t) o->euv.nx * o->euv.ny; // < 2^62
+        ok = nxy <= n_bytes / sizeof(double) && (size_t) o->euv.nv <= n_bytes / sizeof(double) / nxy;
+        if (ok)
+            o->golden_image = o->copy<double>(c, nxy * (size_t) o->euv.nv);
+    }
     if (ok && c.ok && c.take<unsigned char>())
         o->golden_I_ang = o->copy<double>(c, (size_t) o->euv.na * o->euv.nb);
     ok = ok && c.ok && c.pos == n_bytes;
@@ -256,6 +267,10 @@ int rtb200_parse_dat(const void *bytes, size_t n_bytes, rtb200_problem **problem
         *golden_I_ang = o->golden_I_ang;
     *problem = &o->p;
     return RTB200_OK;
+    } catch (...) {
+        delete o;
+        return RTB200_ERR_FORMAT;
+    }
 }
 
 void rtb200_free_problem(rtb200_problem *problem)

@@ -37,6 +37,7 @@ struct FailState {
 
 struct DevProblem {
     const DevPlane *planes; // [N]
+    const PlaneLite *lite;  // [N] what the march's cell look-up starts from (staged in shared memory)
     int N, K, method, use_emis;
     float dz0, c;
     double scale;

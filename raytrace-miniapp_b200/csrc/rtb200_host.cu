@@ -89,6 +89,12 @@ struct rtb200_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr; // uploads the lineshape tables beside the running march
     cudaEvent_t gv_ready = nullptr;
+    // Ordering between calls that may use different streams (the caller's stream of
+    // rtb200_launch*, the context's own stream, the copy stream): every launch ends with
+    // launch_done, every staging with stage_done, and whatever touches the shared arenas
+    // (blob, lineshape tables, hand-off, work counter, failure state) next waits for them.
+    cudaEvent_t stage_done = nullptr, launch_done = nullptr;
+    bool have_launch_done = false;
     std::string err;
     // staging
     PinBuf h_blob, h_gv;
@@ -123,10 +129,8 @@ struct rtb200_ctx {
     rtb200_timings last;
     int launches = 0;
     bool count_steps = false;
-    bool use_fused = false; // opt-in (RTB200_FUSED=1): measured slower than the two-kernel path
-    bool flat_march = true;
     bool ieee_div = false; // never take the reciprocal-table division path (ddiv_by)
-    int march_blocks = 0; // grid of the persistent march on this device
+    int march_blocks = 0; // grid of the persistent march; 0 = resident CTAs x SMs (tuning override)
     unsigned long long *d_work = nullptr;
     size_t handoff_bytes = (size_t) 4096 << 20; // B200 has 180 GB: one chunk for every shipped / synthetic size
 };
@@ -179,6 +183,24 @@ void collect_timing(rtb200_ctx *ctx)
     t.march_steps = ctx->h_fail ? ctx->h_fail->march_steps : 0;
 }
 
+// The kernels read seed->f[4][k] for every frequency bin k < nv and interpolate in the four
+// spatial / angular tables: reject tables that are missing or too short.
+int validate_seed(rtb200_ctx *ctx, const rtb200_seed *s, int nv)
+{
+    if (!s)
+        return RTB200_OK;
+    for (int d = 0; d < 5; d++)
+        if (s->dim[d] < (d < 4 ? 2 : 1) || !s->x[d] || !s->f[d]) {
+            ctx->err = "invalid seed (NULL table or fewer than 2 points per axis)";
+            return RTB200_ERR_ARG;
+        }
+    if (s->dim[4] != nv) {
+        ctx->err = "seed spectrum length differs from the number of frequency bins";
+        return RTB200_ERR_ARG;
+    }
+    return RTB200_OK;
+}
+
 // check_grid (src/RayTraceImage.cpp:237-242)
 bool grid_error(int n, double dx, const double *x)
 {
@@ -198,6 +220,8 @@ int validate(rtb200_ctx *ctx, const rtb200_problem *p, unsigned flags)
         ctx->err = "seed given without seed_beam";
         return RTB200_ERR_ARG;
     }
+    if (int rs = validate_seed(ctx, p->seed, p->euv_beam->nv))
+        return rs;
     const rtb200_beam &e = *p->euv_beam;
     if (!(flags & RTB200_FLAG_NO_LIMITS)) { // src/RayTraceImage.cpp:229-232
         if (p->N > RTB200_N_MAX) {
@@ -284,6 +308,14 @@ int stage_impl(rtb200_ctx *ctx, const rtb200_problem *p, bool explicit_rays, int
                double scale, bool defer_gv = false)
 {
     RTB_CUDA(cudaSetDevice(ctx->device));
+    // a staging that fails part-way must not leave the previous one "staged": its buffers may
+    // already have been freed or overwritten
+    ctx->staged = false;
+    ctx->gv_pending = nullptr;
+    if (ctx->have_launch_done) { // kernels of an earlier launch (any stream) still read the arenas
+        RTB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->launch_done, 0));
+        RTB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->launch_done, 0));
+    }
     DevProblem tmp;
     GvBlob gvb{ nullptr, nullptr, false, 0 };
     const size_t bytes = pack_problem(*p, explicit_rays, method, scale, nullptr, nullptr, tmp, &gvb);
@@ -299,8 +331,11 @@ int stage_impl(rtb200_ctx *ctx, const rtb200_problem *p, bool explicit_rays, int
     ctx->gv_pending = defer_gv ? p : nullptr;
     if (ctx->ieee_div) {
         DevPlane *hp = reinterpret_cast<DevPlane *>(ctx->h_blob.p + ((const char *) ctx->prob.planes - ctx->d_blob.p));
-        for (int i = 0; i < ctx->prob.N; i++)
+        PlaneLite *hl = reinterpret_cast<PlaneLite *>(ctx->h_blob.p + ((const char *) ctx->prob.lite - ctx->d_blob.p));
+        for (int i = 0; i < ctx->prob.N; i++) {
             hp[i].fast_div = 0;
+            hl[i].flags &= ~2;
+        }
     }
     ctx->ev_h2d.first = new_event(ctx, ctx->stream);
     RTB_CUDA(cudaMemsetAsync(ctx->d_fail, 0, sizeof(FailState), ctx->stream));
@@ -310,8 +345,8 @@ int stage_impl(rtb200_ctx *ctx, const rtb200_problem *p, bool explicit_rays, int
         RTB_CUDA(cudaMemcpyAsync(ctx->d_gv.p, ctx->h_gv.p, gvb.bytes, cudaMemcpyHostToDevice,
                                  ctx->stream));
     ctx->ev_h2d.second = new_event(ctx, ctx->stream);
+    RTB_CUDA(cudaEventRecord(ctx->stage_done, ctx->stream));
     ctx->have_h2d = true;
-    ctx->staged = true;
     const DevProblem &P = ctx->prob;
     if (!explicit_rays) {
         ctx->staged_pixels = (long long) P.snx * P.sny;
@@ -329,6 +364,7 @@ int stage_impl(rtb200_ctx *ctx, const rtb200_problem *p, bool explicit_rays, int
         ctx->staged_rays = 0;
         ctx->owner_ok = false;
     }
+    ctx->staged = true;
     return RTB200_OK;
 }
 
@@ -349,19 +385,8 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
     const DevProblem &P = ctx->prob;
     if (pix1 <= pix0)
         return RTB200_OK;
-    if (ctx->owner_ok && !out.Iv && !out.error && ctx->use_fused && row_stride == 1) {
-        int rg = flush_gv(ctx, st);
-        if (rg)
-            return rg;
-        const size_t e0 = new_event(ctx, st);
-        if (launch_trace_ase_fused(P, pix0, pix1, out, st)) {
-            const size_t e1 = new_event(ctx, st);
-            ctx->ev_integ.push_back({ e0, e1 }); // one kernel: reported under integrate_ms
-            ctx->launches += 1;
-            RTB_CUDA(cudaGetLastError());
-            return RTB200_OK;
-        }
-    }
+    if (ctx->have_launch_done) // the hand-off arena and the work counter are shared by all launches
+        RTB_CUDA(cudaStreamWaitEvent(st, ctx->launch_done, 0));
     const int S = (P.N - 1) * RTB_N_SUB;
     const bool need_exit = P.method != 1;
     const size_t per_slot = (size_t) std::max(S, 1) * sizeof(SegRec) + sizeof(unsigned) +
@@ -382,7 +407,7 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
         c.row_off = row_off;
         c.row_stride = row_stride;
         const size_t e0 = new_event(ctx, st);
-        launch_march(P, c, false, h, ctx->d_fail, ctx->count_steps, st, ctx->d_work, ctx->flat_march, ctx->march_blocks);
+        launch_march(P, c, false, h, ctx->d_fail, ctx->count_steps, st, ctx->d_work, ctx->march_blocks);
         const size_t e1m = new_event(ctx, st);
         rc = flush_gv(ctx, st); // host packs the lineshape tables while the march runs
         if (rc)
@@ -398,6 +423,8 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
         ctx->launches += 2;
     }
     RTB_CUDA(cudaGetLastError());
+    RTB_CUDA(cudaEventRecord(ctx->launch_done, st));
+    ctx->have_launch_done = true;
     return RTB200_OK;
 }
 
@@ -463,7 +490,7 @@ int rtb200_create(int device, rtb200_ctx **out)
     auto fail = [&](cudaError_t e) {
         (void) e;
         cudaGetLastError();
-        delete ctx;
+        rtb200_destroy(ctx);
         return RTB200_ERR_CUDA;
     };
     cudaError_t e;
@@ -475,6 +502,10 @@ int rtb200_create(int device, rtb200_ctx **out)
         return fail(e);
     if ((e = cudaEventCreateWithFlags(&ctx->gv_ready, cudaEventDisableTiming)) != cudaSuccess)
         return fail(e);
+    if ((e = cudaEventCreateWithFlags(&ctx->stage_done, cudaEventDisableTiming)) != cudaSuccess)
+        return fail(e);
+    if ((e = cudaEventCreateWithFlags(&ctx->launch_done, cudaEventDisableTiming)) != cudaSuccess)
+        return fail(e);
     if ((e = cudaMalloc((void **) &ctx->d_fail, sizeof(FailState))) != cudaSuccess)
         return fail(e);
     if ((e = cudaMallocHost((void **) &ctx->h_fail, sizeof(FailState))) != cudaSuccess)
@@ -482,15 +513,12 @@ int rtb200_create(int device, rtb200_ctx **out)
     if ((e = cudaMalloc((void **) &ctx->d_work, sizeof(unsigned long long))) != cudaSuccess)
         return fail(e);
     std::memset(ctx->h_fail, 0, sizeof(FailState));
-    ctx->march_blocks = march_persistent_blocks();
+    if (const char *s = getenv("RTB200_MARCH_BLOCKS")) // tuning: grid of the persistent march
+        ctx->march_blocks = std::max(1, atoi(s));
     if (const char *s = getenv("RTB200_HANDOFF_MB"))
         ctx->handoff_bytes = (size_t) std::max(1, atoi(s)) << 20;
     if (const char *s = getenv("RTB200_COUNT_STEPS"))
         ctx->count_steps = atoi(s) != 0;
-    if (const char *s = getenv("RTB200_FUSED"))
-        ctx->use_fused = atoi(s) != 0;
-    if (const char *s = getenv("RTB200_FLAT_MARCH"))
-        ctx->flat_march = atoi(s) != 0;
     if (const char *s = getenv("RTB200_IEEE_DIV")) // tests: plain IEEE divisions by the cell widths
         ctx->ieee_div = atoi(s) != 0;
     *out = ctx;
@@ -534,6 +562,10 @@ void rtb200_destroy(rtb200_ctx *ctx)
         cudaStreamDestroy(ctx->copy_stream);
     if (ctx->gv_ready)
         cudaEventDestroy(ctx->gv_ready);
+    if (ctx->stage_done)
+        cudaEventDestroy(ctx->stage_done);
+    if (ctx->launch_done)
+        cudaEventDestroy(ctx->launch_done);
     delete ctx;
 }
 
@@ -565,16 +597,11 @@ int rtb200_launch(rtb200_ctx *ctx, int64_t pix_begin, int64_t pix_end, double *d
     }
     RTB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : ctx->stream;
-    if (st != ctx->stream) { // order after the staging upload
-        cudaEvent_t e;
-        RTB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        RTB_CUDA(cudaEventRecord(e, ctx->stream));
-        RTB_CUDA(cudaStreamWaitEvent(st, e, 0));
-        RTB_CUDA(cudaEventDestroy(e));
-    }
+    if (st != ctx->stream) // order after the staging upload
+        RTB_CUDA(cudaStreamWaitEvent(st, ctx->stage_done, 0));
     if (ctx->ev_used > 64 + 3 * 4096) // a long series of launches on one staging: keep the pool bounded
         reset_timing(ctx);
-    Outputs out{ d_image, d_I_ang, nullptr, nullptr, ctx->d_fail };
+    Outputs out{ d_image, d_I_ang, nullptr, nullptr, ctx->d_fail, 0 };
     return launch_pixels(ctx, pix_begin, pix_end, out, st);
 }
 
@@ -589,18 +616,13 @@ int rtb200_launch_rows(rtb200_ctx *ctx, int row_offset, int row_stride, double *
     }
     RTB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : ctx->stream;
-    if (st != ctx->stream) { // order after the staging upload
-        cudaEvent_t e;
-        RTB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        RTB_CUDA(cudaEventRecord(e, ctx->stream));
-        RTB_CUDA(cudaStreamWaitEvent(st, e, 0));
-        RTB_CUDA(cudaEventDestroy(e));
-    }
+    if (st != ctx->stream) // order after the staging upload
+        RTB_CUDA(cudaStreamWaitEvent(st, ctx->stage_done, 0));
     if (ctx->ev_used > 64 + 3 * 4096)
         reset_timing(ctx);
     const DevProblem &P = ctx->prob;
     const long long rows = P.sny > row_offset ? (P.sny - row_offset + row_stride - 1) / row_stride : 0;
-    Outputs out{ d_image, d_I_ang, nullptr, nullptr, ctx->d_fail };
+    Outputs out{ d_image, d_I_ang, nullptr, nullptr, ctx->d_fail, 0 };
     return launch_pixels(ctx, 0, rows * P.snx, out, st, row_offset, row_stride);
 }
 
@@ -653,7 +675,7 @@ int rtb200_create_image(rtb200_ctx *ctx, const rtb200_problem *problem, unsigned
     RTB_CUDA(ctx->d_iang.reserve(n_ang));
     RTB_CUDA(cudaMemsetAsync(ctx->d_image.p, 0, n_img * sizeof(double), ctx->stream));
     RTB_CUDA(cudaMemsetAsync(ctx->d_iang.p, 0, n_ang * sizeof(double), ctx->stream));
-    Outputs out{ ctx->d_image.p, ctx->d_iang.p, nullptr, nullptr, ctx->d_fail };
+    Outputs out{ ctx->d_image.p, ctx->d_iang.p, nullptr, nullptr, ctx->d_fail, 0 };
     rc = launch_pixels(ctx, 0, ctx->staged_pixels, out, ctx->stream);
     if (rc == RTB200_OK)
         rc = flush_gv(ctx, ctx->stream); // nothing was launched (no source pixels): finish the staging
@@ -756,7 +778,7 @@ int launch_list(rtb200_ctx *ctx, size_t n_rays, const Outputs &out_all, bool kee
         if (out.error)
             out.error += a;
         const size_t e0 = new_event(ctx, ctx->stream);
-        launch_march(P, c, true, h, ctx->d_fail, ctx->count_steps, ctx->stream, ctx->d_work, ctx->flat_march, ctx->march_blocks);
+        launch_march(P, c, true, h, ctx->d_fail, ctx->count_steps, ctx->stream, ctx->d_work, ctx->march_blocks);
         const size_t e1 = new_event(ctx, ctx->stream);
         launch_integrate_scatter(P, c, true, h, out, ctx->stream);
         const size_t e2 = new_event(ctx, ctx->stream);
@@ -810,7 +832,7 @@ int rtb200_trace_rays(rtb200_ctx *ctx, int N, const rtb200_beam *beam,
         rc = upload_rays(ctx, rays, n_rays);
         if (rc)
             return rc;
-        Outputs out{ ctx->d_image.p, ctx->d_iang.p, nullptr, nullptr, ctx->d_fail };
+        Outputs out{ ctx->d_image.p, ctx->d_iang.p, nullptr, nullptr, ctx->d_fail, 0 };
         rc = launch_list(ctx, n_rays, out, false);
         if (rc)
             return rc;
@@ -864,6 +886,8 @@ int rtb200_calc_rays(rtb200_ctx *ctx, int N, double dz, const rtb200_gain_plane 
             ctx->err = "rtb200_calc_rays: invalid gain plane";
             return RTB200_ERR_ARG;
         }
+    if (int rs = validate_seed(ctx, seed, K))
+        return rs;
     reset_timing(ctx);
     new_event(ctx, ctx->stream);
     int rc = stage_impl(ctx, &p, true, method, 1.0);
@@ -877,7 +901,7 @@ int rtb200_calc_rays(rtb200_ctx *ctx, int N, double dz, const rtb200_gain_plane 
         return rc;
     RTB_CUDA(ctx->d_Iv.reserve(n_rays * (size_t) K));
     RTB_CUDA(ctx->d_err.reserve(n_rays));
-    Outputs out{ nullptr, nullptr, ctx->d_Iv.p, ctx->d_err.p, ctx->d_fail };
+    Outputs out{ nullptr, nullptr, ctx->d_Iv.p, ctx->d_err.p, ctx->d_fail, 0 };
     rc = launch_list(ctx, n_rays, out, true);
     if (rc)
         return rc;
@@ -945,6 +969,8 @@ int rtb200_calc_ray_paths(rtb200_ctx *ctx, int N, double dz, const rtb200_gain_p
             ctx->err = "rtb200_calc_ray_paths: invalid gain plane";
             return RTB200_ERR_ARG;
         }
+    if (int rs = validate_seed(ctx, seed, K))
+        return rs;
     rtb200_beam beam;
     std::memset(&beam, 0, sizeof(beam));
     beam.nv = K;
@@ -983,7 +1009,7 @@ int rtb200_calc_ray_paths(rtb200_ctx *ctx, int N, double dz, const rtb200_gain_p
     ck.ray1 = (long long) n_rays;
     ck.rays = ctx->d_rays.p;
     ck.tans = ctx->d_tans.p;
-    launch_march(ctx->prob, ck, true, h, ctx->d_fail, false, ctx->stream, ctx->d_work, true, ctx->march_blocks);
+    launch_march(ctx->prob, ck, true, h, ctx->d_fail, false, ctx->stream, ctx->d_work, ctx->march_blocks);
     launch_path_intensity(ctx->prob, ck, h, ctx->d_path_I.p, ctx->d_err.p, ctx->stream);
     ctx->launches += 2;
     RTB_CUDA(cudaGetLastError());

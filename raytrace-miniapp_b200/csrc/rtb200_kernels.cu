@@ -1,8 +1,9 @@
 // rtb200_kernels.cu — hand-written sm_100a kernels of the image-formation path.
 //
-//   march_kernel               one thread per ray: refractive march through the gain planes
-//                              (FP32, bit-exact with the reference), hands gvl/evl/ivl per
-//                              (segment, sub-segment) to the integration through L2.
+//   march_flat_kernel          persistent grid, lane = ray: refractive march through the gain
+//                              planes as a flat state machine with batched refills (FP32 +
+//                              mixed FP64, bit-exact with the reference); hands gvl/evl/ivl per
+//                              (segment, sub-segment) to the integration through L2 / HBM.
 //   integrate_ase_owner_kernel one CTA per source pixel, one warp per ray, lanes = frequency
 //                              bins: ASE gain + emission integration (FP64), per-pixel spectrum
 //                              accumulated in registers (no atomics), I_ang by warp-shuffle
@@ -154,10 +155,15 @@ __device__ float atanf_fdlibm(float x)
 // ------------------------------------------------------------------------------------------
 // march
 // ------------------------------------------------------------------------------------------
+// Writes the hand-off record of one (segment, sub-segment) of ray slot L; with PATH also the
+// RAY_DEBUG trajectory points (rtb200_calc_ray_paths).  Holds no state of its own: the record
+// address is formed from the slot number when a record is emitted (once per ~25 trips).
 template <bool PATH>
 struct GlobalSinkT {
-    SegRec *seg;
-    float2 *path; // RAY_DEBUG trajectory of this ray (rtb200_calc_ray_paths); unused unless PATH
+    SegRec *seg;  // hand-off arena
+    float2 *path; // trajectories [slot][S + 1]; unused unless PATH
+    unsigned L;
+    int S;
     __device__ __forceinline__ void operator()(int idx, float gvl, float evl, int cell) const
     {
         int4 v;
@@ -165,85 +171,52 @@ struct GlobalSinkT {
         v.y = __float_as_int(evl);
         v.z = cell;
         v.w = 0;
-        *reinterpret_cast<int4 *>(&seg[idx]) = v;
+        *reinterpret_cast<int4 *>(&seg[(size_t) L * (size_t) S + (size_t) idx]) = v;
     }
     __device__ __forceinline__ void point(int idx, float x, float y) const
     {
         if (PATH)
-            path[idx] = make_float2(x, y);
+            path[(size_t) L * (size_t) (S + 1) + (size_t) idx] = make_float2(x, y);
     }
 };
-typedef GlobalSinkT<false> GlobalSink;
 
-template <bool LIST, bool COUNT>
-__global__ void __launch_bounds__(128) march_kernel(const DevProblem P, const Chunk c,
-                                                    const Handoff h, FailState *fail)
+// Source coordinates of ray slot L (grid mode: decoded from the slot number; list mode: the
+// uploaded ray) and the host-evaluated tangents of its angles.  `active` is false for the
+// padding slots of a strided worker's last pixel.
+template <bool LIST>
+__device__ __forceinline__ bool slot_source(const DevProblem &P, const Chunk &c, unsigned L, float &rx,
+                                            float &ry, float &ra, float &rb, float &ta, float &tb)
 {
-    const long long L = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    const int S = (P.N - 1) * RTB_N_SUB;
-    float rx, ry, ra, rb, ta, tb;
     if (LIST) {
-        if (L >= c.ray1 - c.ray0)
-            return;
         const float4 r = __ldg(&c.rays[c.ray0 + L]);
         const float2 t = __ldg(&c.tans[c.ray0 + L]);
         rx = r.x, ry = r.y, ra = r.z, rb = r.w, ta = t.x, tb = t.y;
-    } else {
-        const long long npix = c.pix1 - c.pix0;
-        if (L >= npix * P.ab_max)
-            return;
-        const long long p = phys_pixel(P, c, c.pix0 + L / P.ab_max);
-        const int t = (int) (L % P.ab_max);
-        const PixelRays pr = pixel_rays(P, p);
-        if (t >= pr.cnt) {
-            h.meta[L] = RTB_META_INACTIVE;
-            return;
-        }
-        const int ab = pr.ab0 + t * (int) P.n_parallel;
-        const int k = ab / P.snb, m = ab % P.snb;
-        rx = __ldg(&P.sxf[pr.i]);
-        ry = __ldg(&P.syf[pr.j]);
-        ra = __ldg(&P.saf[k]);
-        rb = __ldg(&P.sbf[m]);
-        ta = __ldg(&P.tanA[k]);
-        tb = __ldg(&P.tanB[m]);
+        return true;
     }
-    GlobalSink sink{ h.seg + L * S, nullptr };
-    MarchResult res;
-    unsigned steps = 0;
-    march_ray(P.planes, P.N, P.method, P.dz0, P.c, P.use_emis != 0, rx, ry, ta, tb, sink, res,
-              steps);
-    unsigned meta = (unsigned) res.seg_lo | ((unsigned) res.seg_hi << 12);
-    if (res.escaped)
-        meta |= RTB_META_ESCAPED;
-    if (lt_0p01(fmul(res.s.z, res.s.z))) { // error -1 (RayTraceImageHelper.h:515-516)
-        meta |= RTB_META_INVALID;
-        report_failure(fail, 1, rx, ry, ra, rb);
-    } else if (h.exit_ray) {
-        float4 e;
-        e.x = res.pos.x;
-        e.y = res.pos.y;
-        e.z = fmul(atanf_fdlibm(fdiv(res.s.x, res.s.z)), 1e3f);
-        e.w = fmul(atanf_fdlibm(fdiv(res.s.y, res.s.z)), 1e3f);
-        h.exit_ray[L] = e;
-    }
-    h.meta[L] = meta;
-    if (COUNT) {
-        unsigned tot = steps;
-        for (int o = 16; o > 0; o >>= 1)
-            tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        if ((threadIdx.x & 31) == 0)
-            atomicAdd(&fail->march_steps, (unsigned long long) tot);
-    }
+    const unsigned lq = L / (unsigned) P.ab_max; // slots fit 32 bits
+    const long long p = phys_pixel(P, c, c.pix0 + lq);
+    const int t = (int) (L - lq * (unsigned) P.ab_max);
+    const PixelRays pr = pixel_rays(P, p);
+    const bool active = t < pr.cnt;
+    const int ab = pr.ab0 + t * (int) P.n_parallel;
+    const int k = active ? ab / P.snb : 0, mm = active ? ab % P.snb : 0;
+    rx = __ldg(&P.sxf[pr.i]);
+    ry = __ldg(&P.syf[pr.j]);
+    ra = __ldg(&P.saf[k]);
+    rb = __ldg(&P.sbf[mm]);
+    ta = __ldg(&P.tanA[k]);
+    tb = __ldg(&P.tanB[mm]);
+    return active;
 }
 
 // Persistent march: a fixed grid of warps pulls ray slots from a global counter.  Lane = ray,
-// flat state machine (rtb200_march_flat.cuh); a lane whose ray has finished immediately claims
-// the next unprocessed slot (one warp-aggregated atomic per refill), so lanes stay busy although
+// flat state machine (rtb200_march_flat.cuh); a lane whose ray has finished claims the next
+// unprocessed slot (one warp-aggregated atomic per run of slots), so lanes stay busy although
 // the number of steps per ray spans 1..~600 and more than half of the rays of ASE_medium leave
-// the plasma early.
+// the plasma early.  The plane descriptors every cell look-up starts from and the sub-segment
+// limits are staged in shared memory once per CTA.
 #ifndef RTB_MARCH_MINBLOCKS
-#define RTB_MARCH_MINBLOCKS 4
+#define RTB_MARCH_MINBLOCKS 6
 #endif
 #ifndef RTB_MARCH_CHUNK
 #define RTB_MARCH_CHUNK 32
@@ -251,33 +224,51 @@ __global__ void __launch_bounds__(128) march_kernel(const DevProblem P, const Ch
 #ifndef RTB_REFILL_MIN
 #define RTB_REFILL_MIN 6
 #endif
-template <bool LIST, bool COUNT, bool PATH = false>
-__global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(const DevProblem P, const Chunk c,
-                                                         const Handoff h, FailState *fail,
-                                                         unsigned long long *work)
+#define RTB_MARCH_THREADS 128
+template <bool LIST, bool PATH>
+__global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
+    march_flat_kernel(const DevProblem P, const Chunk c, const Handoff h, FailState *fail,
+                      unsigned long long *work, const int count_steps)
 {
+    extern __shared__ __align__(16) unsigned char march_smem[];
+    __shared__ float s_zt[2 * RTB_N_SUB];
+    PlaneLite *s_planes = reinterpret_cast<PlaneLite *>(march_smem); // [N]
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(P.lite);
+        int4 *dst = reinterpret_cast<int4 *>(march_smem);
+        const int n16 = P.N * (int) (sizeof(PlaneLite) / 16);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x)
+            dst[i] = __ldg(src + i);
+    }
+    MarchConsts K;
+    march_consts(K, s_zt, P.N, P.method, P.c, P.use_emis != 0);
+    if (threadIdx.x < RTB_N_SUB)
+        march_sub_limits(s_zt, threadIdx.x, P.dz0);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int S = (P.N - 1) * RTB_N_SUB;
-    const long long n_slots = LIST ? (c.ray1 - c.ray0) : (c.pix1 - c.pix0) * P.ab_max;
-    const bool use_emis = P.use_emis != 0;
+    // slot counts of one chunk fit 31 bits (the host sizes chunks that way)
+    const unsigned n_slots = (unsigned) (LIST ? (c.ray1 - c.ray0) : (c.pix1 - c.pix0) * P.ab_max);
     FlatMarch m;
-    m.phase = PH_DONE;
+    m.st = PH_DONE;
     m.steps = 0;
     bool dead = false, exhausted = false;
-    long long L = 0, run_next = 0, run_end = 0;
-    float rx = 0.f, ry = 0.f, ra = 0.f, rb = 0.f;
+    unsigned L = 0, run_next = 0, run_end = 0;
     unsigned total_steps = 0;
-    GlobalSinkT<PATH> sink{ h.seg, nullptr };
     bool pending = false; // a marched ray whose hand-off entry has not been closed yet
     // Closes the lane's finished ray: meta word, failure report, exit ray (the two atanf of the
     // seeded path).  Runs at the lane's next refill, i.e. for RTB_REFILL_MIN or more lanes at a
     // time, instead of right after the trip in which a single lane happened to finish.
     auto finalize = [&]() {
-        unsigned meta = (unsigned) m.seg_lo | ((unsigned) m.seg_hi << 12);
-        if (m.escaped)
+        int lo, hi;
+        flat_visited_range(m, K, lo, hi);
+        unsigned meta = (unsigned) lo | ((unsigned) hi << 12);
+        if (flat_escaped(m))
             meta |= RTB_META_ESCAPED;
         if (lt_0p01(fmul(m.s.z, m.s.z)) || m.steps > (1u << 22)) { // error -1 (:515-516)
             meta |= RTB_META_INVALID;
+            float rx, ry, ra, rb, ta, tb;
+            slot_source<LIST>(P, c, L, rx, ry, ra, rb, ta, tb);
             report_failure(fail, 1, rx, ry, ra, rb);
         } else if (h.exit_ray) {
             float4 e;
@@ -292,12 +283,12 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
         pending = false;
     };
     for (;;) {
-        const bool need = m.phase == PH_DONE && !dead;
+        const bool need = flat_phase(m) == PH_DONE && !dead;
         const unsigned want = __ballot_sync(0xffffffffu, need);
         // Refills run for at least RTB_REFILL_MIN lanes at a time (or when the warp has nothing
         // else to do): the ~200 instructions of a ray start are issued for the whole warp.
         if (want != 0u && (RTB_REFILL_MIN <= 1 || __popc(want) >= RTB_REFILL_MIN ||
-                           __ballot_sync(0xffffffffu, m.phase != PH_DONE) == 0u)) {
+                           __ballot_sync(0xffffffffu, flat_phase(m) != PH_DONE) == 0u)) {
             // The warp owns a run of RTB_MARCH_CHUNK consecutive slots and hands them to its
             // lanes; one atomic per run instead of one per refill, and the rays a warp marches
             // together are neighbours (same source pixel, adjacent angles), so they cross the
@@ -307,15 +298,13 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
                 if (lane == 0)
                     first = atomicAdd(work, (unsigned long long) RTB_MARCH_CHUNK);
                 first = __shfl_sync(0xffffffffu, first, 0);
-                run_next = (long long) first;
-                run_end = run_next + RTB_MARCH_CHUNK < n_slots ? run_next + RTB_MARCH_CHUNK : n_slots;
-                if (run_next >= n_slots) {
+                run_next = first < (unsigned long long) n_slots ? (unsigned) first : n_slots;
+                run_end = n_slots - run_next > (unsigned) RTB_MARCH_CHUNK ? run_next + RTB_MARCH_CHUNK : n_slots;
+                if (run_next >= n_slots)
                     exhausted = true;
-                    run_end = run_next;
-                }
             }
-            const long long mine = run_next + __popc(want & ((1u << lane) - 1u));
-            const long long after = run_next + __popc(want);
+            const unsigned mine = run_next + __popc(want & ((1u << lane) - 1u));
+            const unsigned after = run_next + __popc(want);
             if (need && pending)
                 finalize();
             if (need) {
@@ -323,47 +312,25 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
                     dead = exhausted; // otherwise: served from the next run on the next trip
                 } else {
                     L = mine;
-                    float ta, tb;
-                    bool active = true;
-                    if (LIST) {
-                        const float4 r = __ldg(&c.rays[c.ray0 + L]);
-                        const float2 t = __ldg(&c.tans[c.ray0 + L]);
-                        rx = r.x, ry = r.y, ra = r.z, rb = r.w, ta = t.x, tb = t.y;
-                    } else {
-                        const unsigned lq = (unsigned) L / (unsigned) P.ab_max; // slots fit 32 bits
-                        const long long p = phys_pixel(P, c, c.pix0 + lq);
-                        const int t = (int) ((unsigned) L - lq * (unsigned) P.ab_max);
-                        const PixelRays pr = pixel_rays(P, p);
-                        active = t < pr.cnt;
-                        const int ab = pr.ab0 + t * (int) P.n_parallel;
-                        const int k = active ? ab / P.snb : 0, mm = active ? ab % P.snb : 0;
-                        rx = __ldg(&P.sxf[pr.i]);
-                        ry = __ldg(&P.syf[pr.j]);
-                        ra = __ldg(&P.saf[k]);
-                        rb = __ldg(&P.sbf[mm]);
-                        ta = __ldg(&P.tanA[k]);
-                        tb = __ldg(&P.tanB[mm]);
-                    }
+                    float rx, ry, ra, rb, ta, tb;
+                    const bool active = slot_source<LIST>(P, c, L, rx, ry, ra, rb, ta, tb);
                     if (!active) {
                         h.meta[L] = RTB_META_INACTIVE;
                     } else {
-                        sink.seg = h.seg + L * S;
-                        if (PATH) { // trajectory start point (:419-426)
-                            const int N2 = S + 1;
-                            sink.path = h.path + L * N2;
-                            sink.path[P.method == 1 ? S : 0] = make_float2(rx, ry);
-                        }
-                        flat_init(m, P.planes, P.N, P.method, P.dz0, rx, ry, ta, tb);
-                        pending = m.phase != PH_DONE;
-                        if (!pending) // N == 1: nothing to march
-                            h.meta[L] = 0u;
+                        if (PATH) // trajectory start point (:419-426)
+                            h.path[(size_t) L * (size_t) (S + 1) + (size_t) (P.method == 1 ? S : 0)] =
+                                make_float2(rx, ry);
+                        flat_init(m, s_planes, K, rx, ry, ta, tb);
+                        // (N == 1: nothing to march, but the ray is still closed by finalize():
+                        // exit ray = start ray, error -1 test, RayTraceImageHelper.h:515-521)
+                        pending = true;
                     }
                 }
             }
             run_next = after < run_end ? after : run_end;
         }
         const unsigned dead_mask = __ballot_sync(0xffffffffu, dead);
-        if (__ballot_sync(0xffffffffu, m.phase != PH_DONE) == 0u) {
+        if (__ballot_sync(0xffffffffu, flat_phase(m) != PH_DONE) == 0u) {
             if (dead_mask == 0xffffffffu)
                 break;
             continue;
@@ -371,18 +338,19 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
         // Inner loop: trips until enough lanes have finished for a batched refill (or the
         // warp has run dry).  Keeping the refill code out of this loop keeps its live ranges
         // out of the hot path.
+        GlobalSinkT<PATH> sink{ h.seg, h.path, L, S };
         for (;;) {
             // every lane takes the trip (finished lanes fall through): see flat_trip
-            const bool was_active = m.phase != PH_DONE;
-            flat_trip(m, P.planes, P.N, P.method, P.dz0, P.c, use_emis, sink);
+            const bool was_active = flat_phase(m) != PH_DONE;
+            flat_trip(m, s_planes, K, sink);
             if (was_active && m.steps > (1u << 22))
-                m.phase = PH_DONE; // hang guard: reported as an invalid ray below
-            const unsigned idle = __ballot_sync(0xffffffffu, m.phase == PH_DONE);
+                flat_set_phase(m, PH_DONE); // hang guard: reported as an invalid ray
+            const unsigned idle = __ballot_sync(0xffffffffu, flat_phase(m) == PH_DONE);
             if (idle == 0xffffffffu || (__popc(idle & ~dead_mask) >= RTB_REFILL_MIN))
                 break;
         }
     }
-    if (COUNT) {
+    if (count_steps) {
         unsigned tot = total_steps;
         for (int o = 16; o > 0; o >>= 1)
             tot += __shfl_xor_sync(0xffffffffu, tot, o);
@@ -391,45 +359,41 @@ __global__ void __launch_bounds__(128, RTB_MARCH_MINBLOCKS) march_flat_kernel(co
     }
 }
 
+template <bool LIST, bool PATH>
+static void launch_march_t(const DevProblem &P, const Chunk &c, const Handoff &h, FailState *fail,
+                           bool count_steps, cudaStream_t st, unsigned long long *work,
+                           int persistent_blocks, long long n)
+{
+    const size_t smem = sizeof(PlaneLite) * (size_t) P.N;
+    auto kern = march_flat_kernel<LIST, PATH>;
+    if (smem > 40 * 1024) // deep stacks of planes (hundreds): opt in to the large carve-out
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    long long blocks = persistent_blocks;
+    if (blocks <= 0) { // resident CTAs per SM (occupancy) x SMs of the current device
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RTB_MARCH_THREADS, smem);
+        blocks = (long long) std::max(1, per_sm) * std::max(1, sms);
+    }
+    blocks = std::min(blocks, (n + RTB_MARCH_THREADS - 1) / RTB_MARCH_THREADS);
+    cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
+    kern<<<(unsigned) blocks, RTB_MARCH_THREADS, smem, st>>>(P, c, h, fail, work, count_steps ? 1 : 0);
+}
+
 void launch_march(const DevProblem &P, const Chunk &c, bool list_mode, const Handoff &h,
                   FailState *fail, bool count_steps, cudaStream_t st, unsigned long long *work,
-                  bool flat, int persistent_blocks)
+                  int persistent_blocks)
 {
     const long long n = list_mode ? (c.ray1 - c.ray0) : (c.pix1 - c.pix0) * P.ab_max;
     if (n <= 0)
         return;
-    const int threads = 128;
-    if (flat) {
-        long long blocks = persistent_blocks > 0 ? persistent_blocks : 148 * 4;
-        blocks = std::min(blocks, (n + threads - 1) / threads);
-        cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
-        if (list_mode && h.path) { // trajectories (rtb200_calc_ray_paths)
-            march_flat_kernel<true, false, true><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, fail, work);
-        } else if (list_mode) {
-            if (count_steps)
-                march_flat_kernel<true, true><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, fail, work);
-            else
-                march_flat_kernel<true, false><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, fail, work);
-        } else {
-            if (count_steps)
-                march_flat_kernel<false, true><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, fail, work);
-            else
-                march_flat_kernel<false, false><<<(unsigned) blocks, threads, 0, st>>>(P, c, h, fail, work);
-        }
-        return;
-    }
-    const unsigned blocks = (unsigned) ((n + threads - 1) / threads);
-    if (list_mode) {
-        if (count_steps)
-            march_kernel<true, true><<<blocks, threads, 0, st>>>(P, c, h, fail);
-        else
-            march_kernel<true, false><<<blocks, threads, 0, st>>>(P, c, h, fail);
-    } else {
-        if (count_steps)
-            march_kernel<false, true><<<blocks, threads, 0, st>>>(P, c, h, fail);
-        else
-            march_kernel<false, false><<<blocks, threads, 0, st>>>(P, c, h, fail);
-    }
+    if (list_mode && h.path) // trajectories (rtb200_calc_ray_paths)
+        launch_march_t<true, true>(P, c, h, fail, count_steps, st, work, persistent_blocks, n);
+    else if (list_mode)
+        launch_march_t<true, false>(P, c, h, fail, count_steps, st, work, persistent_blocks, n);
+    else
+        launch_march_t<false, false>(P, c, h, fail, count_steps, st, work, persistent_blocks, n);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -884,15 +848,43 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, RTB_OWNER_MINBLOCKS)
         part[warp][q * 32 + lane] = pix[q];
     __syncthreads();
     const int pi = __ldg(&P.pixI[pr.i]), pj = __ldg(&P.pixJ[pr.j]);
-    if (pi < 0 || pj < 0)
+    if (!o.compact && (pi < 0 || pj < 0))
         return;
+    // destination pixel, or (compact) the launch's logical pixel
+    const size_t opix = o.compact ? (size_t) (c.pix0 + blockIdx.x) : (size_t) pi + (size_t) pj * P.nx;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         double sum = 0.0;
 #pragma unroll
         for (int w = 0; w < RTB_OWNER_WARPS; w++)
             sum += part[w][k];
-        o.image[(size_t) K * ((size_t) pi + (size_t) pj * P.nx) + k] = sum;
+        o.image[(size_t) K * opix + k] = sum;
     }
+}
+
+// One CTA per source row j: row j was traced by device j % world as its compact row j / world.
+__global__ void __launch_bounds__(256) unpermute_rows_kernel(const DevProblem P, const double *gathered, int world,
+                                                             long long rows_per_dev, double *image)
+{
+    const int j = blockIdx.x;
+    const int pj = __ldg(&P.pixJ[j]);
+    if (pj < 0)
+        return;
+    const int K = P.K;
+    const double *src = gathered + ((size_t) (j % world) * (size_t) rows_per_dev + (size_t) (j / world)) * (size_t) P.snx * K;
+    const int n = P.snx * K;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int i = e / K, k = e - i * K;
+        const int pi = __ldg(&P.pixI[i]);
+        if (pi >= 0)
+            image[(size_t) K * ((size_t) pi + (size_t) pj * P.nx) + k] = src[e];
+    }
+}
+
+void launch_unpermute_rows(const DevProblem &P, const double *gathered, int world, long long rows_per_dev,
+                           double *image, cudaStream_t st)
+{
+    if (P.sny > 0)
+        unpermute_rows_kernel<<<(unsigned) P.sny, 256, 0, st>>>(P, gathered, world, rows_per_dev, image);
 }
 
 void launch_integrate_ase_owner(const DevProblem &P, const Chunk &c, const Handoff &h,
@@ -913,251 +905,6 @@ void launch_integrate_ase_owner(const DevProblem &P, const Chunk &c, const Hando
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Fused ASE kernel: march + frequency integration + binning in ONE launch, no global hand-off.
-//
-// One CTA per source pixel.  Each warp repeatedly claims a batch of RB rays of the pixel and
-//   (1) marches them, lane = ray, flat state machine (rtb200_march_flat.cuh) with refill: a
-//       lane whose ray has finished (58% of ASE_medium's rays escape early) immediately takes
-//       the next ray of the batch, so lanes stay busy until the batch is exhausted;
-//       gvl / evl / ivl go to the warp's private shared-memory slab [record][ray];
-//   (2) integrates them, lane = frequency bin, one ray after the other, reading the records
-//       back as shared-memory broadcasts and the lineshape rows gv[cell][k] as coalesced
-//       read-only loads; the pixel spectrum accumulates in registers, I_ang through a
-//       warp-shuffle reduction and one FP64 atomic per ray.
-// Warps of one SM are in different phases at any time, so the FP32/XU-heavy march and the
-// FP64-heavy integration overlap on the SM's pipes.
-// ------------------------------------------------------------------------------------------
-struct SmemSink {
-    float *gvl, *evl;
-    int *cell;
-    int rb, slot;
-    __device__ __forceinline__ void operator()(int idx, float g, float e, int c) const
-    {
-        gvl[idx * rb + slot] = g;
-        evl[idx * rb + slot] = e;
-        cell[idx * rb + slot] = c;
-    }
-    __device__ __forceinline__ void point(int, float, float) const {}
-};
-
-#define RTB_FUSED_WARPS 8
-
-template <int KS>
-__global__ void __launch_bounds__(RTB_FUSED_WARPS * 32, 2)
-    trace_ase_fused_kernel(const DevProblem P, const long long pix0, const int RB, const Outputs o)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double part[RTB_FUSED_WARPS][KS * 32];
-    __shared__ double exp_tab[64];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int S = (P.N - 1) * RTB_N_SUB;
-    const int K = P.K;
-    // dynamic shared memory: gv row pointers of the planes, then one slab per warp
-    const float **s_gv = reinterpret_cast<const float **>(smem_raw);
-    const size_t slab_words = (size_t) RB * (3 * S + 1);
-    float *slab = reinterpret_cast<float *>(smem_raw + ((sizeof(float *) * P.N + 15) & ~size_t(15))) +
-                  (size_t) warp * slab_words;
-    float *s_gvl = slab, *s_evl = slab + (size_t) RB * S;
-    int *s_cell = reinterpret_cast<int *>(slab + (size_t) 2 * RB * S);
-    unsigned *s_meta = reinterpret_cast<unsigned *>(slab + (size_t) 3 * RB * S);
-    for (int i = threadIdx.x; i < P.N; i += blockDim.x)
-        s_gv[i] = P.planes[i].gv;
-    load_exp_table(exp_tab); // includes __syncthreads()
-    const ArrayConsts KC{ P.kfp, exp_tab };
-
-    const long long p = pix0 + blockIdx.x;
-    const PixelRays pr = pixel_rays(P, p);
-    const float rx = __ldg(&P.sxf[pr.i]), ry = __ldg(&P.syf[pr.j]);
-    const bool use_emis = P.use_emis != 0;
-    double pix[KS], dv2[KS];
-    int koff[KS];
-#pragma unroll
-    for (int q = 0; q < KS; q++) {
-        pix[q] = 0.0;
-        const int k = lane + 32 * q;
-        dv2[q] = k < K ? __ldg(&P.dv2[k]) : 0.0;
-        koff[q] = min(k, K - 1);
-    }
-
-    // Batches are assigned to warps statically (b = warp, warp + 8, ...) so that the order in
-    // which a pixel's rays are summed, and therefore the image, is bit-reproducible.
-    for (int b = warp;; b += RTB_FUSED_WARPS) {
-        const int base = b * RB;
-        if (base >= pr.cnt)
-            break;
-        const int nb = min(RB, pr.cnt - base);
-
-        // ================= (1) march: lane = ray, refill from the batch =================
-        {
-            FlatMarch m;
-            m.phase = PH_DONE;
-            SmemSink sink{ s_gvl, s_evl, s_cell, RB, 0 };
-            int next = 0; // warp-uniform: first unclaimed ray of the batch
-            int ka = 0, kb = 0;
-            for (unsigned trip = 0; trip < (1u << 24); ++trip) {
-                const bool need = m.phase == PH_DONE;
-                const unsigned want = __ballot_sync(0xffffffffu, need);
-                if (want != 0u && next < nb) {
-                    if (need) {
-                        const int idx = next + __popc(want & ((1u << lane) - 1u));
-                        if (idx < nb) {
-                            sink.slot = idx;
-                            const int ab = pr.ab0 + (base + idx) * (int) P.n_parallel;
-                            ka = ab / P.snb;
-                            kb = ab % P.snb;
-                            flat_init(m, P.planes, P.N, 1, P.dz0, rx, ry, __ldg(&P.tanA[ka]),
-                                      __ldg(&P.tanB[kb]));
-                        }
-                    }
-                    next += __popc(want);
-                }
-                if (__ballot_sync(0xffffffffu, m.phase != PH_DONE) == 0u)
-                    break;
-                {
-                    const bool was_active = m.phase != PH_DONE;
-                    flat_trip(m, P.planes, P.N, 1, P.dz0, P.c, use_emis, sink);
-                    if (was_active && m.phase == PH_DONE) {
-                        unsigned meta = (unsigned) m.seg_lo | ((unsigned) m.seg_hi << 12);
-                        if (m.escaped)
-                            meta |= RTB_META_ESCAPED;
-                        if (lt_0p01(fmul(m.s.z, m.s.z))) { // error -1 (:515-516)
-                            meta |= RTB_META_INVALID;
-                            report_failure(o.fail, 1, rx, ry, __ldg(&P.saf[ka]), __ldg(&P.sbf[kb]));
-                        }
-                        s_meta[sink.slot] = meta;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-
-        // ================= (2) integrate: lane = frequency bin, ray after ray =================
-        for (int r = 0; r < nb; r++) {
-            const unsigned meta = s_meta[r];
-            if (meta & RTB_META_INVALID)
-                continue;
-            const int lo = meta & 0xfff, hi = (meta >> 12) & 0xfff;
-            double Iv[KS];
-#pragma unroll
-            for (int q = 0; q < KS; q++)
-                Iv[q] = 0.0;
-            for (int sgm = lo; sgm < hi; sgm++) {
-                const float gvl = s_gvl[sgm * RB + r], evl = s_evl[sgm * RB + r];
-                if (gvl == 0.0f && evl == 0.0f)
-                    continue; // gl = el = 0: the update is the identity
-                const float *row = s_gv[sgm / RTB_N_SUB + 1] + (size_t) s_cell[sgm * RB + r] * K;
-                float g[KS];
-#pragma unroll
-                for (int q = 0; q < KS; q++)
-                    g[q] = __ldg(row + koff[q]);
-#pragma unroll
-                for (int q = 0; q < KS; q++) {
-                    const float glf = __fmul_rn(gvl, g[q]);
-                    const float elf = __fmul_rn(evl, g[q]);
-                    const float ag = fabsf(glf);
-                    const bool small = ag < 1e-3f; // == (fabs((double) glf) < 1e-3)
-                    const unsigned b_small = __ballot_sync(0xffffffffu, small);
-                    const unsigned b_odd = __ballot_sync(0xffffffffu, !(ag < 700.0f));
-                    const double gl = (double) glf, el = (double) elf;
-                    if (b_odd != 0u) {
-                        Iv[q] = ase_update_library(Iv[q], gl, el);
-                    } else {
-                        double a = 0.0, bb = 0.0;
-                        if (b_small != 0u)
-                            a = ase_update_small(Iv[q], gl, el, KC);
-                        if (b_small != 0xffffffffu)
-                            bb = ase_update_large(Iv[q], gl, el, rcp_approx(glf), KC);
-                        Iv[q] = small ? a : bb;
-                    }
-                }
-            }
-            bool neg = false, nan = false;
-#pragma unroll
-            for (int q = 0; q < KS; q++) {
-                neg = neg || Iv[q] < 0.0;
-                nan = nan || Iv[q] != Iv[q];
-            }
-            const bool any_neg = __any_sync(0xffffffffu, neg);
-            const bool any_nan = __any_sync(0xffffffffu, nan);
-            const int ab = pr.ab0 + (base + r) * (int) P.n_parallel;
-            const int ka = ab / P.snb, kb = ab % P.snb;
-            if (any_neg || any_nan) {
-                if (lane == 0)
-                    report_failure(o.fail, any_neg ? 2 : 3, rx, ry, P.saf[ka], P.sbf[kb]);
-                continue;
-            }
-            double w = 0.0;
-#pragma unroll
-            for (int q = 0; q < KS; q++) {
-                w += dv2[q] * Iv[q];
-                pix[q] += Iv[q] * P.scale;
-            }
-            w = warp_sum(w);
-            const int ba = __ldg(&P.binA[ka]), bb = __ldg(&P.binB[kb]);
-            if (lane == 0 && ba >= 0 && bb >= 0)
-                atomicAdd(&o.I_ang[ba + bb * P.na], w);
-        }
-        __syncwarp();
-    }
-#pragma unroll
-    for (int q = 0; q < KS; q++)
-        part[warp][q * 32 + lane] = pix[q];
-    __syncthreads();
-    const int pi = __ldg(&P.pixI[pr.i]), pj = __ldg(&P.pixJ[pr.j]);
-    if (pi < 0 || pj < 0)
-        return;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        double sum = 0.0;
-#pragma unroll
-        for (int w = 0; w < RTB_FUSED_WARPS; w++)
-            sum += part[w][k];
-        o.image[(size_t) K * ((size_t) pi + (size_t) pj * P.nx) + k] = sum;
-    }
-}
-
-size_t fused_smem_bytes(const DevProblem &P, int RB)
-{
-    const int S = (P.N - 1) * RTB_N_SUB;
-    return ((sizeof(float *) * P.N + 15) & ~size_t(15)) +
-           (size_t) RTB_FUSED_WARPS * RB * (3 * S + 1) * sizeof(float);
-}
-
-// Returns false when the problem does not fit the fused kernel (K > 128 or the per-warp slabs
-// exceed shared memory): the caller then uses the two-kernel path.
-bool launch_trace_ase_fused(const DevProblem &P, long long pix0, long long pix1, const Outputs &o,
-                            cudaStream_t st)
-{
-    const long long npix = pix1 - pix0;
-    if (npix <= 0)
-        return true;
-    const int ks = (P.K + 31) / 32;
-    if (ks > 4 || P.N < 2)
-        return false;
-    int RB = 64;
-    if (fused_smem_bytes(P, RB) > 100 * 1024)
-        RB = 32;
-    const size_t smem = fused_smem_bytes(P, RB);
-    if (smem > 200 * 1024)
-        return false;
-    const unsigned blocks = (unsigned) npix;
-    const int threads = RTB_FUSED_WARPS * 32;
-#define RTB_LAUNCH_FUSED(KS_)                                                                   \
-    do {                                                                                        \
-        cudaFuncSetAttribute(trace_ase_fused_kernel<KS_>,                                       \
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);          \
-        trace_ase_fused_kernel<KS_><<<blocks, threads, smem, st>>>(P, pix0, RB, o);             \
-    } while (0)
-    switch (ks) {
-    case 1: RTB_LAUNCH_FUSED(1); break;
-    case 2: RTB_LAUNCH_FUSED(2); break;
-    case 3: RTB_LAUNCH_FUSED(3); break;
-    default: RTB_LAUNCH_FUSED(4); break;
-    }
-#undef RTB_LAUNCH_FUSED
-    return true;
-}
-
 // getIndex (RayTraceImageCPU.cpp:11-16) on the device, for the exit ray: -1 outside the grid
 // +- half a cell, else findfirstsingle(x, n, y - dx/2) = the first index with x[idx] >= Y
 // (0 below the grid, n above it).  The euv grids are uniform (validated), so the index is
@@ -1173,9 +920,11 @@ __device__ __forceinline__ int dev_get_index(int n, const double *x, double dx, 
         return 0;
     if (Y > xn)
         return n;
+    if (!(Y > x0)) // Y == x[0]: the bisection never returns 0 for Y >= x[0] (hi stops at 1)
+        return n > 1 ? 1 : 0;
     int k = (int) ceil((Y - x0) * (1.0 / dx)); // guess (1/dx: dx is warp-uniform per grid)
-    k = k < 0 ? 0 : (k > n - 1 ? n - 1 : k);
-    while (k > 0 && __ldg(&x[k - 1]) >= Y)
+    k = k < 1 ? 1 : (k > n - 1 ? n - 1 : k);
+    while (k > 1 && __ldg(&x[k - 1]) >= Y)
         --k;
     while (k < n - 1 && !(__ldg(&x[k]) >= Y))
         ++k;
@@ -1704,16 +1453,6 @@ void launch_fdiv_check(unsigned b_first, unsigned b_count, int ea, int eb, int v
                        unsigned long long *out, cudaStream_t st)
 {
     fdiv_check_kernel<<<148 * 16, 256, 0, st>>>(b_first, b_count, ea, eb, variant, out);
-}
-
-// Grid of the persistent march: resident CTAs per SM (occupancy) x SMs of the current device.
-int march_persistent_blocks()
-{
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, march_flat_kernel<false, false>, 128, 0);
-    return std::max(1, per_sm) * std::max(1, sms);
 }
 
 void launch_fp64_peak(double *out, int iters, cudaStream_t st, int *blocks, int *threads)

@@ -31,14 +31,18 @@ struct Outputs {
     double *Iv;      // per-ray dump [slots*K] (rtb200_calc_rays) or null
     int *error;      // per-ray error code dump or null
     FailState *fail; // never null
+    // Owner kernel only: image holds the chunk's LOGICAL pixels back to back (pixel q of the
+    // launch at image[q*K]) instead of the full image in destination order.  This is what one
+    // device of a row-cyclic multi-device launch produces: its rows compacted, ready to be
+    // gathered; rtb200_unpermute_rows puts the gathered rows where they belong.
+    int compact;
 };
 
-// flat = true: persistent flat-state-machine march with refill (work = device counter, reset by
-// the launcher); flat = false: the literal nested form, one thread per ray.
+// Persistent flat-state-machine march with refill (work = device counter, reset by the
+// launcher).  persistent_blocks <= 0: resident CTAs per SM x SMs of the current device.
 void launch_march(const DevProblem &P, const Chunk &c, bool list_mode, const Handoff &h,
                   FailState *fail, bool count_steps, cudaStream_t st, unsigned long long *work,
-                  bool flat, int persistent_blocks);
-int march_persistent_blocks(); // for the current device; cached per context by the host layer
+                  int persistent_blocks);
 // ASE (method 1, emission + gain), grid mode: one CTA per source pixel, the pixel's spectrum is
 // owned by the CTA (plain stores), I_ang by atomics.
 void launch_integrate_ase_owner(const DevProblem &P, const Chunk &c, const Handoff &h,
@@ -47,10 +51,10 @@ void launch_integrate_ase_owner(const DevProblem &P, const Chunk &c, const Hando
 // non-identity owner maps) and/or per-ray dumps.
 void launch_integrate_scatter(const DevProblem &P, const Chunk &c, bool list_mode,
                               const Handoff &h, const Outputs &o, cudaStream_t st);
-// Fused ASE path (march + integration + binning in one launch, shared-memory hand-off).
-// Returns false when the problem does not fit it; the caller falls back to the kernels above.
-bool launch_trace_ase_fused(const DevProblem &P, long long pix0, long long pix1, const Outputs &o,
-                            cudaStream_t st);
+// Gathered compact rows of a row-cyclic launch over `world` devices -> full image in
+// destination order (skips source pixels that own no destination pixel).
+void launch_unpermute_rows(const DevProblem &P, const double *gathered, int world, long long rows_per_dev,
+                           double *image, cudaStream_t st);
 void launch_path_intensity(const DevProblem &P, const Chunk &c, const Handoff &h, float *path_I,
                            int *error, cudaStream_t st);
 void launch_fp64_peak(double *out, int iters, cudaStream_t st, int *blocks, int *threads);

@@ -168,6 +168,31 @@ inline void fill_axis_cells(const double *c, int n, AxisCell *t)
     }
 }
 
+// Cell records of one plane (CellRec, rtb200_march.cuh): record i1 = (k1-1) + (k2-1)*Nx holds
+// the corners i1, i1+1, i1+Nx, i1+Nx+1 in the reference's order (:474-477).  The last row and the
+// last column of the array are never addressed (cells end at Nx-2, Ny-2).
+inline void fill_cell_records(const rtb200_gain_plane &g, CellRec *t)
+{
+    const int Nx = g.Nx, Ny = g.Ny;
+    std::memset(t, 0, sizeof(CellRec) * (size_t) Nx * Ny);
+    for (int j = 0; j + 1 < Ny; j++)
+        for (int i = 0; i + 1 < Nx; i++) {
+            const size_t i1 = (size_t) i + (size_t) j * Nx;
+            const size_t c[4] = { i1, i1 + 1, i1 + (size_t) Nx, i1 + (size_t) Nx + 1 };
+            CellRec r;
+            for (int q = 0; q < 4; q++) {
+                r.nf[q] = (float) g.n[c[q]];
+                r.g0[q] = g.g0[c[q]];
+                r.E0[q] = g.E0 ? g.E0[c[q]] : 0.0f;
+            }
+            r.n10 = g.n[c[1]] - g.n[c[0]];
+            r.n32 = g.n[c[3]] - g.n[c[2]];
+            r.n20 = g.n[c[2]] - g.n[c[0]];
+            r.n31 = g.n[c[3]] - g.n[c[1]];
+            t[i1] = r;
+        }
+}
+
 // Bump allocator over the staging blob.  With host == nullptr it only measures.
 class Blob {
 public:
@@ -241,6 +266,7 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
     // ---- gain planes ------------------------------------------------------------------------
     unsigned gv_absmax = 0u;
     DevPlane *planes = blob.alloc<DevPlane>((size_t) N, &out.planes);
+    PlaneLite *lite = blob.alloc<PlaneLite>((size_t) N, &out.lite);
     for (int ii = 0; ii < N; ii++) {
         const rtb200_gain_plane &g = p.gain[ii];
         const size_t nn = (size_t) g.Nx * g.Ny;
@@ -252,23 +278,18 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
         float *gv = (gvb ? gv_blob : blob).alloc<float>(nn * (size_t) K, &P.gv);
         if (gvb)
             gvb->bytes = gv_blob.size();
-        double *rwx = blob.alloc<double>((size_t) g.Nx, &P.rwx);
-        double *rdx = blob.alloc<double>((size_t) g.Nx, &P.rdx);
-        double *rwy = blob.alloc<double>((size_t) g.Ny, &P.rwy);
-        double *rdy = blob.alloc<double>((size_t) g.Ny, &P.rdy);
         AxisCell *cx = blob.alloc<AxisCell>((size_t) g.Nx, &P.cx);
         AxisCell *cy = blob.alloc<AxisCell>((size_t) g.Ny, &P.cy);
+        CellRec *cell = blob.alloc<CellRec>(nn, &P.cell);
         if (fill) {
             bool ok = true;
             double last_w = 0.0;
             bool last_ok = false;
-            auto recip = [&](const double *c, int n, double *rw, double *rd) {
-                rw[0] = rd[0] = 0.0;
+            auto recip = [&](const double *c, int n) {
                 for (int k = 1; k < n; k++) {
                     const double w = c[k] - c[k - 1];
-                    rw[k] = 1.0 / w;
-                    rd[k] = 1.0 / (double) (float) w;
-                    ok = ok && std::isnormal(rw[k]) && std::isnormal(rd[k]) && std::isnormal(w);
+                    const double rw = 1.0 / w, rd = 1.0 / (double) (float) w;
+                    ok = ok && std::isnormal(rw) && std::isnormal(rd) && std::isnormal(w);
                     // every numerator must divide exactly through the tabulated reciprocal
                     // (neighbouring cells of a grid mostly share their width: test it once)
                     if (w != last_w) {
@@ -278,10 +299,11 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
                     ok = ok && last_ok;
                 }
             };
-            recip(g.x, g.Nx, rwx, rdx);
-            recip(g.y, g.Ny, rwy, rdy);
+            recip(g.x, g.Nx);
+            recip(g.y, g.Ny);
             fill_axis_cells(g.x, g.Nx, cx);
             fill_axis_cells(g.y, g.Ny, cy);
+            fill_cell_records(g, cell);
             P.fast_div = ok ? 1 : 0;
             std::memcpy(x, g.x, sizeof(double) * g.Nx);
             std::memcpy(y, g.y, sizeof(double) * g.Ny);
@@ -316,6 +338,24 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
             P.inv_dxf = (float) P.inv_dx;
             P.inv_dyf = (float) P.inv_dy;
             planes[ii] = P;
+            PlaneLite L;
+            std::memset(&L, 0, sizeof(L));
+            L.cx = P.cx;
+            L.cy = P.cy;
+            L.cell = P.cell;
+            L.full = out.planes + ii;
+            L.x0f = P.x0f;
+            L.inv_dxf = P.inv_dxf;
+            L.y0f = P.y0f;
+            L.inv_dyf = P.inv_dyf;
+            L.r0 = P.range[0];
+            L.r1 = P.range[1];
+            L.r2 = P.range[2];
+            L.r3 = P.range[3];
+            L.Nx = P.Nx;
+            L.Ny = P.Ny;
+            L.flags = (P.abs_y ? 1 : 0) | (P.fast_div ? 2 : 0);
+            lite[ii] = L;
         }
     }
 

@@ -60,17 +60,20 @@ long long hostsim_march(const rtb200_problem *p, long long first, long long coun
         ArraySink sink{ gvl + r * S, evl + r * S, ivl + r * S };
         MarchResult res;
         unsigned steps = 0;
-        if (flat) { // the flat state machine the fused GPU kernel runs
+        if (flat) { // the flat state machine the GPU kernel runs
+            float zt[2 * RTB_N_SUB];
+            for (int iz = 0; iz < RTB_N_SUB; iz++)
+                march_sub_limits(zt, iz, P.dz0);
+            MarchConsts K;
+            march_consts(K, zt, P.N, P.method, P.c, P.use_emis != 0);
             FlatMarch fm;
-            flat_init(fm, P.planes, P.N, P.method, P.dz0, P.sxf[i], P.syf[j], P.tanA[k], P.tanB[m]);
-            while (fm.phase != PH_DONE &&
-                   flat_iterate(fm, P.planes, P.N, P.method, P.dz0, P.c, P.use_emis != 0, sink)) {
+            flat_init(fm, P.lite, K, P.sxf[i], P.syf[j], P.tanA[k], P.tanB[m]);
+            while (flat_phase(fm) != PH_DONE && flat_iterate(fm, P.lite, K, sink)) {
             }
             res.pos = fm.pos;
             res.s = fm.s;
-            res.escaped = fm.escaped;
-            res.seg_lo = fm.seg_lo;
-            res.seg_hi = fm.seg_hi;
+            res.escaped = flat_escaped(fm) ? 1 : 0;
+            flat_visited_range(fm, K, res.seg_lo, res.seg_hi);
             steps = fm.steps;
         } else {
             march_ray(P.planes, P.N, P.method, P.dz0, P.c, P.use_emis != 0, P.sxf[i], P.syf[j],

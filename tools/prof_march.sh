@@ -1,0 +1,6 @@
+# ncu --set full of the march + owner kernels on ASE_medium-synth (one launch each)
+TAG=${1:-r02_a}
+python tools/time_cases.py ASE_medium-synth 2>&1 | tail -1
+ncu --set full --clock-control none --import-source on -k regex:"march_flat|integrate_ase_owner" -s 2 -c 2 \
+    -o gpurun_out/${TAG}_full -f python tools/time_cases.py ASE_medium-synth > gpurun_out/${TAG}_ncu_full.log 2>&1
+tail -2 gpurun_out/${TAG}_ncu_full.log
