@@ -8,8 +8,11 @@ SURVEY.md §8d).  A step is one create_image pass over the workload.
   N = 1  workload = "ASE_medium" of BASELINE.json configs[1].  The real ASE_medium.dat is not in
          the reference checkout (.MISSING_LARGE_BLOBS); the documented synthetic stand-in is
          built from ASE_small (raytrace_miniapp_b200.synth.ase_medium_synth).
-  N > 1  one process per GPU (torchrun), image rows sharded across ranks, image tiles gathered
-         and I_ang reduced over NCCL.  Weak scaling: ny is refined by N so rays/GPU is fixed.
+  N > 1  one process per GPU (torchrun), image rows sharded row-cyclically across ranks, each
+         rank's compact rows all-gathered and I_ang reduced over NCCL.  `value`: weak scaling (ny
+         is refined by N so rays/GPU is fixed).  `strong`: the FIXED ASE_medium image at N GPUs
+         (BASELINE.json: "ASE_medium image time at 1/2/4/8 B200"), and `parity`: that sharded
+         image against the single-GPU one of the same run.
 `value` is timed with inputs resident in HBM (CUDA events on the launching stream, max over
 ranks); `e2e` is the same metric through the reference-facing call with host buffers.
 --impl reference times the reference's own CPU implementation (oracle/_ref, unmodified
@@ -157,10 +160,26 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def lib_hash():
+    """sha256 of the product library that is loaded (first 16 hex digits): profile figures are
+    only quoted next to a run of the very build they were captured from."""
+    import hashlib
+    from raytrace_miniapp_b200 import lib as rl
+    return hashlib.sha256(open(rl.library_path(), "rb").read()).hexdigest()[:16]
+
+
+def ncu_figures():
+    """Static figures of the committed ncu captures (profiles/r02_traffic.json), or {}."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    except Exception:
+        return {}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from raytrace_miniapp_b200 import build as rbuild, dist as rdist, lib as rl
+    from raytrace_miniapp_b200 import abi, build as rbuild, dist as rdist, lib as rl
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
         rbuild.build_library()  # no-op when librtb200.so is newer than its sources
     else:  # the other ranks wait for local rank 0's (normally instantaneous) build
@@ -180,93 +199,183 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    problem, name = workload(world, args.scaling)
-    e = problem.euv_beam
-    seg_per_ray = (problem.N - 1) * 3
-    W_seg = problem.n_rays * seg_per_ray
-    W_upd = W_seg * e.nv
-    ctx = rl.Context(local)
-    n_pix = ctx.stage(problem)  # inputs resident in HBM before the timed region
-    image = torch.zeros(e.nx * e.ny * e.nv, dtype=torch.float64, device=dev)
-    I_ang = torch.zeros(e.na * e.nb, dtype=torch.float64, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.Stream(device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     K, Wm = args.steps, args.warmup
-
-    def step():
-        if world > 1:
-            rdist.sharded_create_image(ctx, problem, image, I_ang)
-        else:
-            image.zero_()
-            I_ang.zero_()
-            ctx.launch(0, n_pix, image, I_ang, stream=torch.cuda.current_stream().cuda_stream)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    with torch.cuda.stream(stream):
-        for _ in range(Wm):
-            flush.zero_()
-            step()
-        ctx.sync()
-        barrier()
-        ctx.reset_timings()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-              for _ in range(K)]
-        if rank == 0:
-            sampler.start()
-        t_wall0 = time.perf_counter()
-        for k in range(K):
-            flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
-            ev[k][0].record()
-            step()
-            ev[k][1].record()
-        ctx.sync()
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
-    tm = ctx.timings()
-    ms_total = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([ms_total, tm["march_ms"], tm["integrate_ms"]], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, march_ms, integ_ms = [float(v) for v in t.cpu()]
-    ms_per_step = ms_total / K
-    value = W_seg / (ms_per_step * 1e-3)
-    launches_per_step = tm["kernel_launches"] // K
-    image_norm = float(torch.linalg.vector_norm(image).cpu())
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.cpu()]
 
-    # ---- end to end through the reference-facing call: host buffers, H2D + D2H inside -------------
+    class Job:
+        """One problem resident on this rank's device, traced whole (world 1) or as this rank's
+        rows of a row-cyclic decomposition followed by the exchange."""
+
+        def __init__(self, problem, ctx, sharded):
+            self.p, self.ctx, self.sharded = problem, ctx, sharded and world > 1
+            e = problem.euv_beam
+            self.n_pix = ctx.stage(problem)  # inputs resident in HBM before any timed region
+            self.info = ctx.staged_info()
+            self.image = torch.zeros(e.nx * e.ny * e.nv, dtype=torch.float64, device=dev)
+            self.I_ang = torch.zeros(e.na * e.nb, dtype=torch.float64, device=dev)
+            self.rows = rdist.RowGather(self.info, world, dev) if self.sharded and self.info["owner"] else None
+
+        def step(self):
+            if self.sharded:
+                rdist.sharded_create_image(self.ctx, self.p, self.image, self.I_ang, rows=self.rows)
+            else:
+                self.image.zero_()
+                self.I_ang.zero_()
+                self.ctx.launch(0, self.n_pix, self.image, self.I_ang,
+                                stream=torch.cuda.current_stream().cuda_stream)
+
+        def exchange_name(self):
+            if not self.sharded:
+                return "single GPU"
+            if self.rows is not None:
+                return ("image rows sharded row-cyclically over %d GPUs; NCCL all_gather of each rank's "
+                        "compact rows (1/%d of the image) + un-permute kernel, all_reduce(sum) of I_ang"
+                        % (world, world))
+            return ("image rows sharded row-cyclically over %d GPUs; NCCL all_reduce(sum) of the "
+                    "full-size partial images and of I_ang" % world)
+
+        def timed(self, steps, warmup):
+            """Device time per step (CUDA events on the launching stream, L2 flushed between
+            steps, barrier + synchronize on both sides), max over ranks; kernel times likewise."""
+            with torch.cuda.stream(stream):
+                for _ in range(warmup):
+                    flush.zero_()
+                    self.step()
+                self.ctx.sync()
+                barrier()
+                self.ctx.reset_timings()
+                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                      for _ in range(steps)]
+                t0 = time.perf_counter()
+                for k in range(steps):
+                    flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
+                    ev[k][0].record()
+                    self.step()
+                    ev[k][1].record()
+                self.ctx.sync()
+                barrier()
+                wall = time.perf_counter() - t0
+            tm = self.ctx.timings()
+            ms = sum(a.elapsed_time(b) for a, b in ev)
+            ms, march, integ = max_over_ranks([ms, tm["march_ms"], tm["integrate_ms"]])
+            return {"ms_per_step": ms / steps, "march_ms": march / steps, "integrate_ms": integ / steps,
+                    "launches": tm["kernel_launches"], "wall_s": wall}
+
+        def e2e(self, ctx2, steps, warmup, h_img, h_ang):
+            """The same step through the host-facing path: host arrays in (pack + H2D inside the
+            timed region), host image / I_ang out (D2H inside), wall clock, max over ranks."""
+            times = []
+            for i in range(warmup + steps):
+                barrier()
+                t0 = time.perf_counter()
+                if not self.sharded:
+                    ctx2.create_image(self.p, image=h_img.numpy(), I_ang=h_ang.numpy())
+                else:
+                    with torch.cuda.stream(stream):
+                        ctx2.stage(self.p, flags=abi.FLAG_LAZY_TABLES)  # every rank stages its own copy
+                        rdist.sharded_create_image(ctx2, self.p, self.image, self.I_ang, rows=self.rows)
+                        if rank == 0:  # the caller's buffers live in one process: one download
+                            h_img.copy_(self.image, non_blocking=True)
+                            h_ang.copy_(self.I_ang, non_blocking=True)
+                        ctx2.sync()
+                barrier()
+                if i >= warmup:
+                    times.append(time.perf_counter() - t0)
+            return max_over_ranks([sum(times) / len(times)])[0]
+
+    ctx, ctx2 = rl.Context(local), rl.Context(local)
+    problem, name = workload(world, args.scaling)
+    e = problem.euv_beam
+    seg_per_ray = (problem.N - 1) * 3
+    W_seg = problem.n_rays * seg_per_ray
+    W_upd = W_seg * e.nv
+    job = Job(problem, ctx, sharded=True)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    main = job.timed(K, Wm)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = main["ms_per_step"]
+    value = W_seg / (ms_per_step * 1e-3)
+    image_norm = float(torch.linalg.vector_norm(job.image).cpu())
+
     h_img = torch.empty(e.nx * e.ny * e.nv, dtype=torch.float64).pin_memory()
     h_ang = torch.empty(e.na * e.nb, dtype=torch.float64).pin_memory()
-    h2d = d2h = 0
-    e2e_times = []
-    ctx2 = rl.Context(local)
-    for i in range(Wm + K):
-        barrier()
-        t0 = time.perf_counter()
-        if world == 1:
-            ctx2.create_image(problem, image=h_img.numpy(), I_ang=h_ang.numpy())
-        else:
-            with torch.cuda.stream(stream):
-                ctx2.stage(problem)
-                rdist.sharded_create_image(ctx2, problem, image, I_ang)
-                h_img.copy_(image, non_blocking=True)
-                h_ang.copy_(I_ang, non_blocking=True)
-                ctx2.sync()
-        barrier()
-        if i >= Wm:
-            e2e_times.append(time.perf_counter() - t0)
+    e2e_s = job.e2e(ctx2, K, Wm, h_img, h_ang)
     gain_bytes = sum(g.x.nbytes + g.y.nbytes + g.n.size * 16 + g.gv.nbytes for g in problem.gain)
     h2d = gain_bytes + 8 * (e.nx + e.ny + e.na + e.nb + e.nv) + 16 * (e.nx + e.ny + e.na + e.nb)
     d2h = h_img.numel() * 8 + h_ang.numel() * 8 + 536
-    te = torch.tensor([sum(e2e_times) / len(e2e_times)], dtype=torch.float64, device=dev)
+
+    # ---- BASELINE.json's second metric: the FIXED ASE_medium image at `world` GPUs (strong
+    # scaling), and the parity of the sharded result with the single-GPU one ----------------------
+    strong = parity = None
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.cpu()[0])
+        fixed, fixed_name = workload(1, "strong")
+        ef = fixed.euv_beam
+        ks, ws = max(3, min(K, 10)), max(3, min(Wm, 3))
+        sj = Job(fixed, rl.Context(local), sharded=True)
+        st = sj.timed(ks, ws)
+        hf_img = torch.empty(ef.nx * ef.ny * ef.nv, dtype=torch.float64).pin_memory()
+        hf_ang = torch.empty(ef.na * ef.nb, dtype=torch.float64).pin_memory()
+        st_e2e = sj.e2e(rl.Context(local), ks, ws, hf_img, hf_ang)
+        sharded_img, sharded_ang = sj.image.clone(), sj.I_ang.clone()
+        single = {"ms_per_step": 0.0}
+        same_bits, ang_err, e2e1 = True, 0.0, 0.0
+        if rank == 0:  # the single-GPU reference of the same problem, on rank 0 alone
+            old_world = world
+            oj = Job(fixed, rl.Context(local), sharded=False)
+            with torch.cuda.stream(stream):
+                for _ in range(ws):
+                    flush.zero_()
+                    oj.step()
+                oj.ctx.sync()
+                torch.cuda.synchronize()
+                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ks)]
+                for k in range(ks):
+                    flush.zero_()
+                    ev[k][0].record()
+                    oj.step()
+                    ev[k][1].record()
+                oj.ctx.sync()
+                torch.cuda.synchronize()
+            single["ms_per_step"] = sum(a.elapsed_time(b) for a, b in ev) / ks
+            c1 = rl.Context(local)
+            t_e = []
+            for i in range(ws + ks):
+                t0 = time.perf_counter()
+                c1.create_image(fixed, image=hf_img.numpy(), I_ang=hf_ang.numpy())
+                if i >= ws:
+                    t_e.append(time.perf_counter() - t0)
+            e2e1 = sum(t_e) / len(t_e)
+            same_bits = bool(torch.equal(sharded_img, oj.image))
+            ang_err = float((torch.linalg.vector_norm(sharded_ang - oj.I_ang) /
+                             torch.linalg.vector_norm(oj.I_ang)).cpu())
+            assert old_world == world
+        barrier()
+        strong = {"workload": fixed_name, "image_time_ms_device": st["ms_per_step"],
+                  "image_time_ms_e2e": st_e2e * 1e3,
+                  "single_gpu_image_time_ms_device": single["ms_per_step"],
+                  "single_gpu_image_time_ms_e2e": e2e1 * 1e3,
+                  "speedup_vs_1": single["ms_per_step"] / st["ms_per_step"] if rank == 0 else None,
+                  "speedup_vs_1_e2e": e2e1 / st_e2e if rank == 0 else None,
+                  "kernel_ms_per_step": {"march": st["march_ms"], "integrate": st["integrate_ms"]},
+                  "steps": ks, "parallelism": sj.exchange_name()}
+        parity = {"checked": "sharded image / I_ang of the fixed ASE_medium-synth at %d GPUs against the "
+                             "single-GPU result computed in this run on rank 0" % world,
+                  "image_bit_identical_to_single_gpu": same_bits, "I_ang_relL2": ang_err}
 
     if rank == 0:
         fp64_peak = ctx.measure_fp64_peak()  # FP64 lane-instr/s (DFMA), measured on this box
@@ -276,70 +385,54 @@ def run_gpu(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        traffic = None
-        executed_per_update = None
-        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["integrate_ase_owner_kernel"]
-            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-            executed_per_update = tj.get("fp64_instr_per_update_executed")
-        except Exception:
-            pass
-        march_prof = {}
-        try:
-            march_prof = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["march_flat_kernel"]
-        except Exception:
-            pass
-        launches_integ = max(1, launches_per_step // 2) * K
-        integ_s = integ_ms * 1e-3
-        upd_local = W_upd / world  # per rank (weak: identical tiles)
-        fp64_instr = upd_local * FP64_INSTR_PER_UPDATE * K
-        achieved_tflops = fp64_instr * 2 / integ_s / 1e12
+        prof = ncu_figures()
+        prof_ok = bool(prof) and prof.get("lib_sha16") == lib_hash()
+        step_s = ms_per_step * 1e-3
+        upd_local = W_upd / world  # per rank (weak: identical shares)
         peak_tflops = fp64_peak * 2 / 1e12
-        # compulsory HBM bytes of one pass: gain planes read once + image / I_ang written once
-        alg_bytes = gain_bytes + image.numel() * 8 / world + I_ang.numel() * 8
-        # Roofline of the dominant pipe of the integration kernel.  `achieved` counts the FP64
-        # instructions the kernel really issues per frequency update (ncu, profiles/
-        # r01_traffic.json); the SURVEY.md 8d convention (the reference formula with the library
-        # exp and divide: 32 per update) is kept beside it - by that count the kernel is past 1.0
-        # of the peak, which only says that its exp / reciprocal are cheaper than the library's.
-        per_upd = executed_per_update if executed_per_update is not None else FP64_INSTR_PER_UPDATE
+        # W_fp64 = frequency updates x 32 FP64 instructions (the reference formula with
+        # the library exp and divide), against the measured DFMA peak, over the WHOLE step: march +
+        # integration.  That is the fraction the north_star's 0.60 target is about.
+        step_tflops = upd_local * FP64_INSTR_PER_UPDATE * 2 / step_s / 1e12
+        integ_tflops = upd_local * FP64_INSTR_PER_UPDATE * 2 / (main["integrate_ms"] * 1e-3) / 1e12
+        alg_bytes = gain_bytes + job.image.numel() * 8 / world + job.I_ang.numel() * 8
+        dominant = "march_flat_kernel" if main["march_ms"] >= main["integrate_ms"] else "integrate_ase_owner_kernel"
+        traffic = None
+        if prof_ok:
+            traffic = sum(prof[k]["dram_bytes_read"] + prof[k]["dram_bytes_write"]
+                          for k in ("march_flat_kernel", "integrate_ase_owner_kernel") if k in prof)
         roofline = {
-            "bound": "fp64", "kernel": "integrate_ase_owner_kernel",
-            "achieved": achieved_tflops * per_upd / FP64_INSTR_PER_UPDATE, "peak": peak_tflops,
-            "unit": "TFLOP/s",
-            "frac": achieved_tflops * per_upd / FP64_INSTR_PER_UPDATE / peak_tflops,
+            "bound": "fp64", "kernel": dominant,
+            "achieved": step_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+            "frac": step_tflops / peak_tflops,
             "traffic": traffic,
-            "traffic_note": "dram read+write bytes per launch (ncu, profiles/r01_traffic.json): the "
-                            "march->integrate hand-off records, not re-reads of the inputs",
-            "convention": "%.2f FP64 instr issued per frequency update (ncu count of this kernel, "
-                          "profiles/r01_traffic.json) x 2 flop x updates / kernel time; peak = DFMA "
-                          "micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 "
-                          "entry).  The kernel is bound by instruction issue (72%% of the issue "
-                          "slots busy, FP64 pipe 47%%)" % per_upd,
-            "survey_convention": {
-                "fp64_instr_per_update": FP64_INSTR_PER_UPDATE, "achieved": achieved_tflops,
-                "frac": achieved_tflops / peak_tflops, "unit": "TFLOP/s",
-                "note": "SURVEY.md 8d fixed convention: the reference formula with library exp and "
-                        "divide; above 1.0 because this kernel's exp / reciprocal need fewer FP64 "
-                        "instructions than that"},
-            "avg_launch_ms": integ_ms / launches_integ,
-            "hbm": {"achieved": alg_bytes * K / integ_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": alg_bytes * K / integ_s / 1e9 / hbm_peak,
-                    "note": "algorithmic bytes only; the path is FP64/issue-bound, not HBM-bound"}}
-        # The march (the larger half of the step) has no pipe roofline: scalar FP32 / mixed FP64
-        # per ray with data-dependent trip counts.  Its bound is instruction issue x SIMT
-        # efficiency; both factors from the committed ncu capture, the rate from this run.
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        if march_prof.get("warp_instr_per_launch") and sms and args.scaling == "weak":
-            issue_peak = sms * 4 * (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
-            rate = march_prof["warp_instr_per_launch"] * K / (march_ms * 1e-3)
-            roofline["march_kernel"] = {
-                "kernel": "march_flat_kernel", "bound": "issue", "unit": "warp-instr/s",
-                "achieved": rate, "peak": issue_peak, "frac": rate / issue_peak,
-                "simt_efficiency": march_prof.get("active_threads_per_instr", 0) / 32.0,
-                "avg_launch_ms": march_ms / launches_integ,
-                "note": "peak = SMs x 4 schedulers x SM clock; instructions per launch from ncu "
-                        "(profiles/r01_traffic.json, N=1 workload; per GPU the same in weak scaling)"}
+            "convention": "SURVEY.md 8d at step level: frequency updates x 32 FP64 instr x 2 flop / "
+                          "device time of the whole step (march + integration); peak = DFMA "
+                          "micro-benchmark of this run (%.3e FP64 lane-instr/s; MEASURED_PEAKS.json has "
+                          "no FP64 entry)" % fp64_peak,
+            "traffic_note": "dram read+write bytes per step of both kernels (ncu --set full of this very "
+                            "library build, profiles/r02_traffic.json): the march->integrate hand-off "
+                            "records, not re-reads of the inputs" if prof_ok else
+                            "null: no ncu capture of this library build is committed (sha mismatch)",
+            "fp64_peak_lane_instr_per_s": fp64_peak,
+            "per_kernel": {
+                "march_flat_kernel": {"ms": main["march_ms"], "share_of_step": main["march_ms"] / ms_per_step,
+                                      "bound": "instruction issue x SIMT efficiency (FP32 / XU scalar "
+                                               "work per ray, no pipe roofline)"},
+                "integrate_ase_owner_kernel": {
+                    "ms": main["integrate_ms"], "share_of_step": main["integrate_ms"] / ms_per_step,
+                    "survey_fraction": integ_tflops / peak_tflops,
+                    "note": "8d convention for this kernel alone; its own exp / reciprocal need fewer "
+                            "FP64 instructions than the library's 32, so this can pass 1.0"}},
+            "hbm": {"achieved": alg_bytes / step_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": alg_bytes / step_s / 1e9 / hbm_peak,
+                    "note": "algorithmic bytes (gain planes in, image / I_ang out) over the step; the "
+                            "path is instruction-issue / FP64 bound, not HBM-bound"}}
+        if prof_ok:  # pipe-busy figures of the same build (static: measured under ncu, not in this run)
+            roofline["ncu_same_build"] = {k: prof[k] for k in prof if k not in ("lib_sha16", "source")}
+        launches_per_step = main["launches"] // K
+        if job.sharded and job.rows is not None:
+            launches_per_step += 1  # the un-permute kernel
         line = {
             "metric": "ray_segments_per_s", "value": value, "unit": "ray-segments/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_per_step,
@@ -347,18 +440,24 @@ def run_gpu(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": name, "rays": problem.n_rays, "ray_segments": W_seg,
                        "frequency_updates": W_upd, "l2": "256 MiB buffer rewritten between timed steps",
-                       "parallelism": "image rows sharded over %d GPU(s), NCCL all_gather(image) + "
-                                      "all_reduce(I_ang)" % world if world > 1 else "single GPU"},
+                       "parallelism": job.exchange_name()},
             "clocks": clocks,
             "e2e": {"value": W_seg / e2e_s, "unit": "ray-segments/s", "image_time_ms": e2e_s * 1e3,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": launches_per_step * K,
             "image_time_ms_device": ms_per_step,
-            "kernel_ms_per_step": {"march": march_ms / K, "integrate": integ_ms / K},
+            "kernel_ms_per_step": {"march": main["march_ms"], "integrate": main["integrate_ms"]},
             "image_l2_norm": image_norm,
+            "lib_sha16": lib_hash(),
             "roofline": roofline,
-            "wall_s_timed_region": t_wall,
+            "wall_s_timed_region": main["wall_s"],
         }
+        if strong is not None:
+            line["strong"] = strong
+            line["parity"] = parity
+        elif args.scaling == "weak":  # N = 1: the fixed image IS the workload
+            line["strong"] = {"workload": name, "image_time_ms_device": ms_per_step,
+                              "image_time_ms_e2e": e2e_s * 1e3, "speedup_vs_1": 1.0, "speedup_vs_1_e2e": 1.0}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 r = reference_cpu(problem, args.cpu_stride or 16, 1, 0)

@@ -48,6 +48,14 @@ extern "C" {
 
 /* Flags for rtb200_create_image / rtb200_trace_rays */
 #define RTB200_FLAG_NO_LIMITS 0x1u /* do not enforce N <= N_MAX, nv < K_MAX */
+/* rtb200_stage only: the lineshape tables (nine tenths of the bytes, read by the integration only)
+ * are packed and uploaded by the first launch, next to its running march kernel, as
+ * rtb200_create_image does.  The rtb200_problem and its arrays must stay valid until that launch
+ * returns. */
+#define RTB200_FLAG_LAZY_TABLES 0x2u
+
+/* Largest number of frequency bins the pixel-owner integration kernel covers in one pass. */
+#define RTB200_OWNER_K_MAX 128
 
 typedef struct rtb200_ray {
     float x, y, a, b;
@@ -167,6 +175,19 @@ int rtb200_stage(rtb200_ctx *ctx, const rtb200_problem *problem, unsigned flags)
 int64_t rtb200_staged_pixels(const rtb200_ctx *ctx);
 int64_t rtb200_staged_rays(const rtb200_ctx *ctx);
 
+/* Shape of the staged problem, for callers that shard it (rtb200_multi, bench.py).
+ * owner = 1: ASE with one source pixel per destination pixel, traced by the pixel-owner kernel:
+ * image rows of different devices are disjoint and can be gathered (rtb200_launch_rows_compact +
+ * rtb200_unpermute_rows); owner = 0 (seeded, or a non-injective pixel map): partial images
+ * overlap and must be summed. */
+typedef struct rtb200_staged {
+    int32_t method, owner;
+    int32_t snx, sny;    /* source grid (euv_beam for ASE, seed_beam for seeded) */
+    int32_t nx, ny, na, nb, nv; /* destination grid */
+    int32_t reserved;
+} rtb200_staged;
+int rtb200_staged_info(const rtb200_ctx *ctx, rtb200_staged *out);
+
 /* Trace the staged problem's source pixels [pix_begin, pix_end) on the context's stream.
  * d_image / d_I_ang are DEVICE pointers to full-size buffers (nx*ny*nv, na*nb doubles).
  * ASE: writes (overwrites) image rows of the owned pixels only and adds into d_I_ang;
@@ -182,12 +203,53 @@ int rtb200_launch(rtb200_ctx *ctx, int64_t pix_begin, int64_t pix_end, double *d
  * at pixel-row granularity, which keeps every pixel's spectrum on one device. */
 int rtb200_launch_rows(rtb200_ctx *ctx, int row_offset, int row_stride, double *d_image,
                        double *d_I_ang, void *cuda_stream);
+/* The same share, written COMPACTLY: d_rows receives the device's rows back to back
+ * (ceil((sny - row_offset) / row_stride) rows of snx*nv doubles, in source-grid order), which is
+ * what a gather over the devices moves: 1/row_stride of the image instead of a full-size buffer
+ * per device.  Only for owner-traced problems (rtb200_staged_info).  d_I_ang: as above. */
+int rtb200_launch_rows_compact(rtb200_ctx *ctx, int row_offset, int row_stride, double *d_rows,
+                               double *d_I_ang, void *cuda_stream);
+/* Puts gathered compact rows where they belong: d_gathered holds `world` blocks of
+ * rows_per_dev*snx*nv doubles (block r = the rows of device r, rows_per_dev >= ceil(sny/world));
+ * d_image is the full image (nx*ny*nv doubles, zeroed by the caller: destination pixels that no
+ * source pixel owns are not written).  The exchange step of the multi-device ASE path; replaces
+ * the sum of full-size partial images of intensity_step_struct::sum_reduce
+ * (src/RayTraceStructures.cpp:1603-1646) by a gather of owned rows. */
+int rtb200_unpermute_rows(rtb200_ctx *ctx, const double *d_gathered, int world, int64_t rows_per_dev,
+                          double *d_image, void *cuda_stream);
 int rtb200_sync(rtb200_ctx *ctx, unsigned *failure_code, rtb200_ray *failed, int max_failed,
                 int *n_failed);
 int rtb200_get_timings(const rtb200_ctx *ctx, rtb200_timings *out);
 /* Forget the launches recorded so far: the timings returned after the next rtb200_sync then
  * cover exactly the launches issued in between (used to time a series of steps). */
 int rtb200_reset_timings(rtb200_ctx *ctx);
+
+/* ---- several devices of one box (single process) --------------------------------------------- */
+
+/* Replaces the reference's `cuda-multigpu` method (src/RayTraceImage.cpp:396-405:
+ * RayTraceImageThreadLoop with one worker per GPU and a host-side sum of partial images; its
+ * cudaSetDevice in the parent thread, :116-119, puts every worker on device 0) and the
+ * application's cross-rank intensity_step_struct::sum_reduce (src/RayTraceStructures.cpp:
+ * 1603-1646).  One context per device, the image sharded by rows (device r of W traces rows r,
+ * r + W, ...), the partial results gathered / reduced to the first device over NVLink by NCCL
+ * (ncclCommInitAll; libnccl.so.2 is bound at run time, n_dev == 1 needs none), one download.
+ * devices == NULL means 0 .. n_dev-1.  On RTB200_ERR_CUDA *out may still be non-NULL so that
+ * rtb200_multi_last_error() can tell why; destroy it either way. */
+typedef struct rtb200_multi rtb200_multi;
+int rtb200_multi_create(const int *devices, int n_dev, rtb200_multi **out);
+void rtb200_multi_destroy(rtb200_multi *m);
+const char *rtb200_multi_last_error(const rtb200_multi *m); /* never NULL */
+int rtb200_multi_device_count(const rtb200_multi *m);
+/* Same contract as rtb200_create_image (host buffers in and out, image / I_ang overwritten).
+ * ASE images are bit-identical to the single-device result (rows are owned, never summed);
+ * I_ang and seeded images are sums of per-device partials (~1e-16 relative). */
+int rtb200_multi_create_image(rtb200_multi *m, const rtb200_problem *problem, unsigned flags,
+                              double *image, double *I_ang, unsigned *failure_code,
+                              rtb200_ray *failed, int max_failed, int *n_failed);
+/* Timings of the last call: per_device[n_dev] (may be NULL), the exchange step on the first
+ * device (NCCL + un-permute) and first event to last event on the first device. */
+int rtb200_multi_get_timings(const rtb200_multi *m, rtb200_timings *per_device, float *exchange_ms,
+                             float *total_ms);
 
 /* ---- wire format ---------------------------------------------------------------------------- */
 

@@ -5,7 +5,7 @@ importable name onto this hyphenated directory).
 """
 from .abi import (BeamGrid, Gain, Problem, SeedProfile, N_SUB, N_MAX, K_MAX, ray_dtype,  # noqa: F401
                   OK, RAYS_FAILED, ERR_LIMITS, ERR_GRID, ERR_CUDA, ERR_ARG, ERR_FORMAT,
-                  FLAG_NO_LIMITS)
+                  FLAG_NO_LIMITS, FLAG_LAZY_TABLES)
 from .datfile import read_dat, write_dat, parse_payload, pack_payload  # noqa: F401
 
 __version__ = "0.1.0"

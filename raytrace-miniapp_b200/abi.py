@@ -13,6 +13,7 @@ N_MAX, K_MAX, N_SUB, N_FAILED_MAX = 20, 100, 3, 32
 OK, RAYS_FAILED = 0, 1
 ERR_LIMITS, ERR_GRID, ERR_CUDA, ERR_ARG, ERR_FORMAT = -1, -2, -3, -4, -5
 FLAG_NO_LIMITS = 0x1
+FLAG_LAZY_TABLES = 0x2
 
 c_double_p = C.POINTER(C.c_double)
 c_float_p = C.POINTER(C.c_float)
@@ -55,6 +56,12 @@ class Timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("march_ms", C.c_float), ("integrate_ms", C.c_float),
                 ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("kernel_launches", C.c_int32),
                 ("reserved", C.c_int32), ("n_rays", C.c_uint64), ("march_steps", C.c_uint64)]
+
+
+class Staged(C.Structure):
+    _fields_ = [("method", C.c_int32), ("owner", C.c_int32), ("snx", C.c_int32), ("sny", C.c_int32),
+                ("nx", C.c_int32), ("ny", C.c_int32), ("na", C.c_int32), ("nb", C.c_int32),
+                ("nv", C.c_int32), ("reserved", C.c_int32)]
 
 
 def _f64(a):

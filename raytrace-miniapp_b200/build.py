@@ -10,11 +10,11 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librtb200.so")
-SOURCES = ["rtb200_kernels.cu", "rtb200_host.cu", "rtb200_dat.cpp"]
+SOURCES = ["rtb200_kernels.cu", "rtb200_host.cu", "rtb200_multi.cu", "rtb200_dat.cpp"]
 HEADERS = ["rtb200_march_flat.cuh", "rtb200_fp64.cuh", "rtb200_exptab.h", "rtb200_math.cuh", "rtb200_march.cuh", "rtb200_device.cuh", "rtb200_kernels.cuh",
            "rtb200_pack.h", os.path.join("..", "..", "include", "rtb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-shared", "-cudart", "static"]
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-shared", "-cudart", "static", "-ldl"]
 
 
 def _nvcc():

@@ -394,7 +394,9 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
     long long pix_per_chunk =
         std::max<long long>(1, (long long) (ctx->handoff_bytes / per_slot) / std::max(P.ab_max, 1));
     pix_per_chunk = std::min(pix_per_chunk, pix1 - pix0);
-    pix_per_chunk = std::min<long long>(pix_per_chunk, ((1LL << 31) - 1) / std::max(P.ab_max, 1)); // 32-bit slots
+    // the kernels count the slots AND the hand-off records of one chunk in 32 bits
+    pix_per_chunk = std::min<long long>(pix_per_chunk, ((1LL << 31) - 1) / std::max(P.ab_max, 1) / std::max(S, 1));
+    pix_per_chunk = std::max<long long>(pix_per_chunk, 1);
     int rc = ensure_handoff(ctx, pix_per_chunk * P.ab_max, need_exit);
     if (rc)
         return rc;
@@ -413,7 +415,7 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
         if (rc)
             return rc;
         const size_t e1 = new_event(ctx, st);
-        if (ctx->owner_ok && !out.Iv && !out.error && P.K <= 128) // one pass of <= 4 bin slots
+        if (ctx->owner_ok && !out.Iv && !out.error && P.K <= RTB200_OWNER_K_MAX) // one pass of <= 4 bin slots
             launch_integrate_ase_owner(P, c, h, out, st);
         else
             launch_integrate_scatter(P, c, false, h, out, st);
@@ -580,7 +582,25 @@ int rtb200_stage(rtb200_ctx *ctx, const rtb200_problem *problem, unsigned flags)
         return rc;
     reset_timing(ctx);
     new_event(ctx, ctx->stream);
-    return stage_impl(ctx, problem, false, 0, 0.0);
+    return stage_impl(ctx, problem, false, 0, 0.0, (flags & RTB200_FLAG_LAZY_TABLES) != 0);
+}
+
+int rtb200_staged_info(const rtb200_ctx *ctx, rtb200_staged *out)
+{
+    if (!ctx || !out || !ctx->staged)
+        return RTB200_ERR_ARG;
+    const DevProblem &P = ctx->prob;
+    out->method = P.method;
+    out->owner = ctx->owner_ok && P.K <= RTB200_OWNER_K_MAX ? 1 : 0;
+    out->snx = P.snx;
+    out->sny = P.sny;
+    out->nx = P.nx;
+    out->ny = P.ny;
+    out->na = P.na;
+    out->nb = P.nb;
+    out->nv = P.K;
+    out->reserved = 0;
+    return RTB200_OK;
 }
 
 int64_t rtb200_staged_pixels(const rtb200_ctx *ctx) { return ctx && ctx->staged ? ctx->staged_pixels : 0; }
@@ -605,13 +625,19 @@ int rtb200_launch(rtb200_ctx *ctx, int64_t pix_begin, int64_t pix_end, double *d
     return launch_pixels(ctx, pix_begin, pix_end, out, st);
 }
 
-int rtb200_launch_rows(rtb200_ctx *ctx, int row_offset, int row_stride, double *d_image,
-                       double *d_I_ang, void *cuda_stream)
+static int launch_rows_impl(rtb200_ctx *ctx, int row_offset, int row_stride, double *d_image,
+                            double *d_I_ang, void *cuda_stream, bool compact)
 {
     if (!ctx || !ctx->staged || !d_image || !d_I_ang || row_stride < 1 || row_offset < 0 ||
         row_offset >= row_stride) {
         if (ctx)
             ctx->err = "rtb200_launch_rows: nothing staged or bad argument";
+        return RTB200_ERR_ARG;
+    }
+    const DevProblem &P = ctx->prob;
+    if (compact && !(ctx->owner_ok && P.K <= RTB200_OWNER_K_MAX)) {
+        ctx->err = "rtb200_launch_rows_compact: the staged problem is not traced by pixel owners "
+                   "(rtb200_staged_info().owner == 0): use rtb200_launch_rows and a sum";
         return RTB200_ERR_ARG;
     }
     RTB_CUDA(cudaSetDevice(ctx->device));
@@ -620,10 +646,39 @@ int rtb200_launch_rows(rtb200_ctx *ctx, int row_offset, int row_stride, double *
         RTB_CUDA(cudaStreamWaitEvent(st, ctx->stage_done, 0));
     if (ctx->ev_used > 64 + 3 * 4096)
         reset_timing(ctx);
-    const DevProblem &P = ctx->prob;
     const long long rows = P.sny > row_offset ? (P.sny - row_offset + row_stride - 1) / row_stride : 0;
-    Outputs out{ d_image, d_I_ang, nullptr, nullptr, ctx->d_fail, 0 };
+    Outputs out{ d_image, d_I_ang, nullptr, nullptr, ctx->d_fail, compact ? 1 : 0 };
     return launch_pixels(ctx, 0, rows * P.snx, out, st, row_offset, row_stride);
+}
+
+int rtb200_launch_rows(rtb200_ctx *ctx, int row_offset, int row_stride, double *d_image,
+                       double *d_I_ang, void *cuda_stream)
+{
+    return launch_rows_impl(ctx, row_offset, row_stride, d_image, d_I_ang, cuda_stream, false);
+}
+
+int rtb200_launch_rows_compact(rtb200_ctx *ctx, int row_offset, int row_stride, double *d_rows,
+                               double *d_I_ang, void *cuda_stream)
+{
+    return launch_rows_impl(ctx, row_offset, row_stride, d_rows, d_I_ang, cuda_stream, true);
+}
+
+int rtb200_unpermute_rows(rtb200_ctx *ctx, const double *d_gathered, int world, int64_t rows_per_dev,
+                          double *d_image, void *cuda_stream)
+{
+    if (!ctx || !ctx->staged || !d_gathered || !d_image || world < 1 ||
+        rows_per_dev < (ctx->prob.sny + world - 1) / world) {
+        if (ctx)
+            ctx->err = "rtb200_unpermute_rows: nothing staged or bad argument";
+        return RTB200_ERR_ARG;
+    }
+    RTB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : ctx->stream;
+    if (st != ctx->stream)
+        RTB_CUDA(cudaStreamWaitEvent(st, ctx->stage_done, 0));
+    launch_unpermute_rows(ctx->prob, d_gathered, world, rows_per_dev, d_image, st);
+    RTB_CUDA(cudaGetLastError());
+    return RTB200_OK;
 }
 
 int rtb200_sync(rtb200_ctx *ctx, unsigned *failure_code, rtb200_ray *failed, int max_failed,
@@ -755,7 +810,7 @@ int launch_list(rtb200_ctx *ctx, size_t n_rays, const Outputs &out_all, bool kee
     long long per_chunk = keep_handoff ? (long long) n_rays
                                        : std::max<long long>(1, (long long) (ctx->handoff_bytes / per_slot));
     per_chunk = std::min<long long>(per_chunk, (long long) n_rays);
-    const long long max_slots = (1LL << 31) - 64; // the kernels count the slots of a chunk in 32 bits
+    const long long max_slots = ((1LL << 31) - 64) / std::max(S, 1); // slots and records of a chunk are counted in 32 bits
     if (keep_handoff && per_chunk > max_slots) {
         ctx->err = "more than 2^31 rays in one call that keeps the per-ray intermediates";
         return RTB200_ERR_LIMITS;

@@ -164,6 +164,7 @@ struct GlobalSinkT {
     float2 *path; // trajectories [slot][S + 1]; unused unless PATH
     unsigned L;
     int S;
+    unsigned rec0; // L*S: record numbers of one chunk fit 32 bits (the host sizes chunks that way)
     __device__ __forceinline__ void operator()(int idx, float gvl, float evl, int cell) const
     {
         int4 v;
@@ -171,7 +172,7 @@ struct GlobalSinkT {
         v.y = __float_as_int(evl);
         v.z = cell;
         v.w = 0;
-        *reinterpret_cast<int4 *>(&seg[(size_t) L * (size_t) S + (size_t) idx]) = v;
+        *reinterpret_cast<int4 *>(&seg[rec0 + (unsigned) idx]) = v;
     }
     __device__ __forceinline__ void point(int idx, float x, float y) const
     {
@@ -216,7 +217,7 @@ __device__ __forceinline__ bool slot_source(const DevProblem &P, const Chunk &c,
 // the plasma early.  The plane descriptors every cell look-up starts from and the sub-segment
 // limits are staged in shared memory once per CTA.
 #ifndef RTB_MARCH_MINBLOCKS
-#define RTB_MARCH_MINBLOCKS 6
+#define RTB_MARCH_MINBLOCKS 5
 #endif
 #ifndef RTB_MARCH_CHUNK
 #define RTB_MARCH_CHUNK 32
@@ -225,14 +226,15 @@ __device__ __forceinline__ bool slot_source(const DevProblem &P, const Chunk &c,
 #define RTB_REFILL_MIN 6
 #endif
 #define RTB_MARCH_THREADS 128
-template <bool LIST, bool PATH>
+#define RTB_ST_HUNG 64u  // gave up on the ray (hang guard): reported as invalid
+#define RTB_ST_DEAD 128u // the lane has no ray and there is none left to claim
+template <bool LIST, bool PATH, bool COUNT>
 __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
     march_flat_kernel(const DevProblem P, const Chunk c, const Handoff h, FailState *fail,
-                      unsigned long long *work, const int count_steps)
+                      unsigned long long *work)
 {
-    extern __shared__ __align__(16) unsigned char march_smem[];
-    __shared__ float s_zt[2 * RTB_N_SUB];
-    PlaneLite *s_planes = reinterpret_cast<PlaneLite *>(march_smem); // [N]
+    extern __shared__ __align__(16) unsigned char march_smem[]; // PlaneLite[N]
+    __shared__ float s_zt[4];
     {
         const int4 *src = reinterpret_cast<const int4 *>(P.lite);
         int4 *dst = reinterpret_cast<int4 *>(march_smem);
@@ -240,11 +242,15 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
         for (int i = threadIdx.x; i < n16; i += blockDim.x)
             dst[i] = __ldg(src + i);
     }
-    MarchConsts K;
-    march_consts(K, s_zt, P.N, P.method, P.c, P.use_emis != 0);
     if (threadIdx.x < RTB_N_SUB)
-        march_sub_limits(s_zt, threadIdx.x, P.dz0);
+        s_zt[threadIdx.x] = march_sub_limit(threadIdx.x, P.dz0);
     __syncthreads();
+    // the shuffles make the shared-memory addresses opaque: otherwise the compiler rebuilds them
+    // from the CTA's shared window (S2R + LEA) at every use
+    MarchConsts K;
+    march_consts(K, __shfl_sync(0xffffffffu, (unsigned) __cvta_generic_to_shared(march_smem), 0),
+                 __shfl_sync(0xffffffffu, (unsigned) __cvta_generic_to_shared(s_zt), 0), P.N, P.method, P.c,
+                 P.use_emis != 0);
     const int lane = threadIdx.x & 31;
     const int S = (P.N - 1) * RTB_N_SUB;
     // slot counts of one chunk fit 31 bits (the host sizes chunks that way)
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
     FlatMarch m;
     m.st = PH_DONE;
     m.steps = 0;
-    bool dead = false, exhausted = false;
+    bool exhausted = false;
     unsigned L = 0, run_next = 0, run_end = 0;
     unsigned total_steps = 0;
     bool pending = false; // a marched ray whose hand-off entry has not been closed yet
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
         unsigned meta = (unsigned) lo | ((unsigned) hi << 12);
         if (flat_escaped(m))
             meta |= RTB_META_ESCAPED;
-        if (lt_0p01(fmul(m.s.z, m.s.z)) || m.steps > (1u << 22)) { // error -1 (:515-516)
+        if (lt_0p01(fmul(m.s.z, m.s.z)) || (m.st & RTB_ST_HUNG)) { // error -1 (:515-516)
             meta |= RTB_META_INVALID;
             float rx, ry, ra, rb, ta, tb;
             slot_source<LIST>(P, c, L, rx, ry, ra, rb, ta, tb);
@@ -279,11 +285,12 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
             h.exit_ray[L] = e;
         }
         h.meta[L] = meta;
-        total_steps += m.steps;
+        if (COUNT)
+            total_steps += m.steps;
         pending = false;
     };
     for (;;) {
-        const bool need = flat_phase(m) == PH_DONE && !dead;
+        const bool need = (m.st & (RTB_ST_PHASE | RTB_ST_DEAD)) == (unsigned) PH_DONE;
         const unsigned want = __ballot_sync(0xffffffffu, need);
         // Refills run for at least RTB_REFILL_MIN lanes at a time (or when the warp has nothing
         // else to do): the ~200 instructions of a ray start are issued for the whole warp.
@@ -309,7 +316,8 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
                 finalize();
             if (need) {
                 if (mine >= run_end) {
-                    dead = exhausted; // otherwise: served from the next run on the next trip
+                    if (exhausted) // otherwise: served from the next run on the next trip
+                        m.st |= RTB_ST_DEAD;
                 } else {
                     L = mine;
                     float rx, ry, ra, rb, ta, tb;
@@ -320,7 +328,7 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
                         if (PATH) // trajectory start point (:419-426)
                             h.path[(size_t) L * (size_t) (S + 1) + (size_t) (P.method == 1 ? S : 0)] =
                                 make_float2(rx, ry);
-                        flat_init(m, s_planes, K, rx, ry, ta, tb);
+                        flat_init(m, K, rx, ry, ta, tb);
                         // (N == 1: nothing to march, but the ray is still closed by finalize():
                         // exit ray = start ray, error -1 test, RayTraceImageHelper.h:515-521)
                         pending = true;
@@ -329,28 +337,28 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
             }
             run_next = after < run_end ? after : run_end;
         }
-        const unsigned dead_mask = __ballot_sync(0xffffffffu, dead);
         if (__ballot_sync(0xffffffffu, flat_phase(m) != PH_DONE) == 0u) {
-            if (dead_mask == 0xffffffffu)
+            if (__all_sync(0xffffffffu, (m.st & RTB_ST_DEAD) != 0u))
                 break;
             continue;
         }
         // Inner loop: trips until enough lanes have finished for a batched refill (or the
         // warp has run dry).  Keeping the refill code out of this loop keeps its live ranges
         // out of the hot path.
-        GlobalSinkT<PATH> sink{ h.seg, h.path, L, S };
-        for (;;) {
+        GlobalSinkT<PATH> sink{ h.seg, h.path, L, S, L * (unsigned) S };
+        for (unsigned trips = 0;; ++trips) { // (warp-uniform counter)
             // every lane takes the trip (finished lanes fall through): see flat_trip
-            const bool was_active = flat_phase(m) != PH_DONE;
-            flat_trip(m, s_planes, K, sink);
-            if (was_active && m.steps > (1u << 22))
-                flat_set_phase(m, PH_DONE); // hang guard: reported as an invalid ray
-            const unsigned idle = __ballot_sync(0xffffffffu, flat_phase(m) == PH_DONE);
-            if (idle == 0xffffffffu || (__popc(idle & ~dead_mask) >= RTB_REFILL_MIN))
+            flat_trip(m, K, sink);
+            // hang guard: no ray takes 2^22 trips; whatever is still marching is given up
+            if (trips > (1u << 22) && flat_phase(m) != PH_DONE)
+                m.st = (m.st | RTB_ST_HUNG | RTB_ST_PHASE); // PH_DONE == all phase bits
+            // lanes that can take a new ray / lanes that are marching
+            const unsigned refill = __ballot_sync(0xffffffffu, (m.st & (RTB_ST_PHASE | RTB_ST_DEAD)) == (unsigned) PH_DONE);
+            if (__popc(refill) >= RTB_REFILL_MIN || __all_sync(0xffffffffu, flat_phase(m) == PH_DONE))
                 break;
         }
     }
-    if (count_steps) {
+    if (COUNT) {
         unsigned tot = total_steps;
         for (int o = 16; o > 0; o >>= 1)
             tot += __shfl_xor_sync(0xffffffffu, tot, o);
@@ -359,13 +367,12 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
     }
 }
 
-template <bool LIST, bool PATH>
+template <bool LIST, bool PATH, bool COUNT>
 static void launch_march_t(const DevProblem &P, const Chunk &c, const Handoff &h, FailState *fail,
-                           bool count_steps, cudaStream_t st, unsigned long long *work,
-                           int persistent_blocks, long long n)
+                           cudaStream_t st, unsigned long long *work, int persistent_blocks, long long n)
 {
     const size_t smem = sizeof(PlaneLite) * (size_t) P.N;
-    auto kern = march_flat_kernel<LIST, PATH>;
+    auto kern = march_flat_kernel<LIST, PATH, COUNT>;
     if (smem > 40 * 1024) // deep stacks of planes (hundreds): opt in to the large carve-out
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     long long blocks = persistent_blocks;
@@ -378,7 +385,7 @@ static void launch_march_t(const DevProblem &P, const Chunk &c, const Handoff &h
     }
     blocks = std::min(blocks, (n + RTB_MARCH_THREADS - 1) / RTB_MARCH_THREADS);
     cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
-    kern<<<(unsigned) blocks, RTB_MARCH_THREADS, smem, st>>>(P, c, h, fail, work, count_steps ? 1 : 0);
+    kern<<<(unsigned) blocks, RTB_MARCH_THREADS, smem, st>>>(P, c, h, fail, work);
 }
 
 void launch_march(const DevProblem &P, const Chunk &c, bool list_mode, const Handoff &h,
@@ -389,11 +396,15 @@ void launch_march(const DevProblem &P, const Chunk &c, bool list_mode, const Han
     if (n <= 0)
         return;
     if (list_mode && h.path) // trajectories (rtb200_calc_ray_paths)
-        launch_march_t<true, true>(P, c, h, fail, count_steps, st, work, persistent_blocks, n);
+        launch_march_t<true, true, false>(P, c, h, fail, st, work, persistent_blocks, n);
+    else if (list_mode && count_steps)
+        launch_march_t<true, false, true>(P, c, h, fail, st, work, persistent_blocks, n);
     else if (list_mode)
-        launch_march_t<true, false>(P, c, h, fail, count_steps, st, work, persistent_blocks, n);
+        launch_march_t<true, false, false>(P, c, h, fail, st, work, persistent_blocks, n);
+    else if (count_steps)
+        launch_march_t<false, false, true>(P, c, h, fail, st, work, persistent_blocks, n);
     else
-        launch_march_t<false, false>(P, c, h, fail, count_steps, st, work, persistent_blocks, n);
+        launch_march_t<false, false, false>(P, c, h, fail, st, work, persistent_blocks, n);
 }
 
 // ------------------------------------------------------------------------------------------

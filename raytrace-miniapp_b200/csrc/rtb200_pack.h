@@ -171,7 +171,8 @@ inline void fill_axis_cells(const double *c, int n, AxisCell *t)
 // Cell records of one plane (CellRec, rtb200_march.cuh): record i1 = (k1-1) + (k2-1)*Nx holds
 // the corners i1, i1+1, i1+Nx, i1+Nx+1 in the reference's order (:474-477).  The last row and the
 // last column of the array are never addressed (cells end at Nx-2, Ny-2).
-inline void fill_cell_records(const rtb200_gain_plane &g, CellRec *t)
+inline void fill_cell_records(const rtb200_gain_plane &g, const AxisCell *cx, const AxisCell *cy,
+                              CellRec *t)
 {
     const int Nx = g.Nx, Ny = g.Ny;
     std::memset(t, 0, sizeof(CellRec) * (size_t) Nx * Ny);
@@ -189,6 +190,12 @@ inline void fill_cell_records(const rtb200_gain_plane &g, CellRec *t)
             r.n32 = g.n[c[3]] - g.n[c[2]];
             r.n20 = g.n[c[2]] - g.n[c[0]];
             r.n31 = g.n[c[3]] - g.n[c[1]];
+            r.xl = cx[i + 1].lo;
+            r.dxd = cx[i + 1].dd;
+            r.rdx = cx[i + 1].rd;
+            r.yl = cy[j + 1].lo;
+            r.dyd = cy[j + 1].dd;
+            r.rdy = cy[j + 1].rd;
             t[i1] = r;
         }
 }
@@ -303,7 +310,7 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
             recip(g.y, g.Ny);
             fill_axis_cells(g.x, g.Nx, cx);
             fill_axis_cells(g.y, g.Ny, cy);
-            fill_cell_records(g, cell);
+            fill_cell_records(g, cx, cy, cell);
             P.fast_div = ok ? 1 : 0;
             std::memcpy(x, g.x, sizeof(double) * g.Nx);
             std::memcpy(y, g.y, sizeof(double) * g.Ny);

@@ -5,9 +5,11 @@ sharded axis): rank r traces the contiguous pixel range tile_bounds(n, world, r)
 image rows exclusively (ASE).  The exchange step that follows the kernels is the one the full
 application performs over MPI (intensity_step_struct::sum_reduce,
 src/RayTraceStructures.cpp:1603-1646), restated for device-resident partials:
-  contiguous tiles, ASE : all_gather of the equal-sized image tiles + all_reduce(sum) of I_ang
-  row-cyclic (default)  : all_reduce(sum) of the full image (rows are disjoint) and of I_ang
-  seeded                : all_reduce(sum) of the full image and of I_ang (scatter binning)
+  row-cyclic ASE (default): every rank writes its rows compactly, all_gather of the compact rows
+                           (1/world of the image per rank), un-permute into the image,
+                           all_reduce(sum) of I_ang
+  contiguous tiles, ASE   : all_gather of the equal-sized image tiles + all_reduce(sum) of I_ang
+  seeded                  : all_reduce(sum) of the full image and of I_ang (scatter binning)
 over NCCL / NVLink on GPUs, gloo in the CPU tests.
 """
 import torch
@@ -54,15 +56,51 @@ def exchange_rows(image, I_ang, group=None):
     return image, I_ang
 
 
-def sharded_create_image(ctx, problem, image, I_ang, group=None, stream=None, cyclic=True):
+def rows_per_rank(n_rows, world):
+    return (n_rows + world - 1) // world
+
+
+def unpermute_rows(gathered, image, n_rows, row_elems, world):
+    """Host-side statement of rtb200_unpermute_rows for identity pixel maps (CPU tests): block r
+    of `gathered` holds the rows r, r + world, ... of the image, compactly."""
+    per = rows_per_rank(n_rows, world)
+    g = gathered.view(world, per, row_elems)
+    img = image.view(n_rows, row_elems)
+    for r in range(world):
+        mine = len(range(r, n_rows, world))
+        img[r::world] = g[r, :mine]
+    return image
+
+
+class RowGather:
+    """Buffers of the row-cyclic ASE exchange (allocated once, reused every step)."""
+
+    def __init__(self, info, world, device):
+        self.per = rows_per_rank(info["sny"], world)
+        n = self.per * info["snx"] * info["nv"]
+        self.part = torch.empty(n, dtype=torch.float64, device=device)
+        self.gathered = torch.empty(n * world, dtype=torch.float64, device=device)
+
+
+def sharded_create_image(ctx, problem, image, I_ang, group=None, stream=None, cyclic=True, rows=None):
     """Stage-free step: `ctx` already holds the staged problem.  Zeroes the buffers, traces this
     rank's share on `stream` (default: torch's current stream) and exchanges.  Asynchronous.
-    cyclic=True: image rows rank, rank + world, ... (balanced; exchange = all_reduce);
+    cyclic=True: image rows rank, rank + world, ... (balanced).  With `rows` (a RowGather; ASE
+    traced by pixel owners) each rank writes its rows compactly and the exchange is an
+    all_gather of 1/world of the image per rank + un-permute; without it every rank fills a
+    full-size buffer and the exchange is an all_reduce (seeded: the partials overlap).
     cyclic=False: one contiguous tile per rank (exchange = all_gather of the tiles)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    image.zero_()
     I_ang.zero_()
     st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+    if cyclic and rows is not None:
+        ctx.launch_rows_compact(rank, world, rows.part, I_ang, stream=st)
+        dist.all_gather_into_tensor(rows.gathered, rows.part, group=group)
+        image.zero_()
+        ctx.unpermute_rows(rows.gathered, world, rows.per, image, stream=st)
+        dist.all_reduce(I_ang, op=dist.ReduceOp.SUM, group=group)
+        return image, I_ang
+    image.zero_()
     if cyclic:
         ctx.launch_rows(rank, world, image, I_ang, stream=st)
         return exchange_rows(image, I_ang, group)

@@ -79,6 +79,18 @@ def load():
     L.rtb200_staged_rays.restype = C.c_int64
     L.rtb200_launch.argtypes = [ctx, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.rtb200_launch_rows.argtypes = [ctx, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.rtb200_launch_rows_compact.argtypes = [ctx, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.rtb200_unpermute_rows.argtypes = [ctx, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+    L.rtb200_staged_info.argtypes = [ctx, P(abi.Staged)]
+    L.rtb200_multi_create.argtypes = [P(C.c_int), C.c_int, P(ctx)]
+    L.rtb200_multi_destroy.argtypes = [ctx]
+    L.rtb200_multi_destroy.restype = None
+    L.rtb200_multi_last_error.argtypes = [ctx]
+    L.rtb200_multi_last_error.restype = C.c_char_p
+    L.rtb200_multi_device_count.argtypes = [ctx]
+    L.rtb200_multi_create_image.argtypes = [ctx, P(abi.CProblem), C.c_uint, C.c_void_p, C.c_void_p,
+                                            P(C.c_uint), P(abi.Ray), C.c_int, P(C.c_int)]
+    L.rtb200_multi_get_timings.argtypes = [ctx, P(abi.Timings), P(C.c_float), P(C.c_float)]
     L.rtb200_sync.argtypes = [ctx, P(C.c_uint), P(abi.Ray), C.c_int, P(C.c_int)]
     L.rtb200_get_timings.argtypes = [ctx, P(abi.Timings)]
     L.rtb200_reset_timings.argtypes = [ctx]
@@ -234,7 +246,7 @@ class Context:
     def stage(self, problem, flags=0):
         cp, keep = problem.c_struct()
         self._check(self.L.rtb200_stage(self.h, C.byref(cp), flags))
-        self._keep = keep
+        self._keep = (cp, keep)  # with FLAG_LAZY_TABLES the library reads them again at the launch
         return self.L.rtb200_staged_pixels(self.h)
 
     @property
@@ -260,6 +272,25 @@ class Context:
             stream = 1  # cudaStreamLegacy
         self._check(self.L.rtb200_launch_rows(self.h, row_offset, row_stride, _addr(d_image),
                                               _addr(d_I_ang), stream))
+
+    def launch_rows_compact(self, row_offset, row_stride, d_rows, d_I_ang, stream=None):
+        """The same share written compactly (its rows back to back): what a gather moves."""
+        if stream is not None and stream == 0:
+            stream = 1  # cudaStreamLegacy
+        self._check(self.L.rtb200_launch_rows_compact(self.h, row_offset, row_stride, _addr(d_rows),
+                                                      _addr(d_I_ang), stream))
+
+    def unpermute_rows(self, d_gathered, world, rows_per_dev, d_image, stream=None):
+        """Gathered compact rows of `world` devices -> full image (zeroed by the caller)."""
+        if stream is not None and stream == 0:
+            stream = 1
+        self._check(self.L.rtb200_unpermute_rows(self.h, _addr(d_gathered), world, rows_per_dev,
+                                                 _addr(d_image), stream))
+
+    def staged_info(self):
+        s = abi.Staged()
+        self._check(self.L.rtb200_staged_info(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in abi.Staged._fields_ if k != "reserved"}
 
     def sync(self, raise_on_failed=True):
         fc, nf = C.c_uint(0), C.c_int(0)
@@ -293,3 +324,58 @@ class Context:
         r = C.c_double(0)
         self._check(self.L.rtb200_measure_fp64_peak(self.h, C.byref(r)))
         return r.value
+
+
+class MultiContext:
+    """Several devices of one box behind one call (rtb200_multi): the reference's `cuda-multigpu`
+    method (src/RayTraceImage.cpp:396-405) with the partial results exchanged over NCCL."""
+
+    def __init__(self, devices):
+        self.L = load()
+        self.h = C.c_void_p()
+        devs = list(range(devices)) if isinstance(devices, int) else list(devices)
+        arr = (C.c_int * len(devs))(*devs)
+        rc = self.L.rtb200_multi_create(arr, len(devs), C.byref(self.h))
+        if rc != abi.OK:
+            msg = self.L.rtb200_multi_last_error(self.h).decode() if self.h else "no usable CUDA devices"
+            self.close()
+            raise RTB200Error(rc, msg)
+        self.n = len(devs)
+
+    def close(self):
+        if self.h:
+            self.L.rtb200_multi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def create_image(self, problem, flags=0, image=None, I_ang=None, raise_on_failed=True):
+        e = problem.euv_beam
+        cp, keep = problem.c_struct()
+        image = np.empty(e.nx * e.ny * e.nv) if image is None else image
+        I_ang = np.empty(e.na * e.nb) if I_ang is None else I_ang
+        _check_out(image, e.nx * e.ny * e.nv, "image")
+        _check_out(I_ang, e.na * e.nb, "I_ang")
+        fc, nf = C.c_uint(0), C.c_int(0)
+        failed = np.zeros(abi.N_FAILED_MAX, abi.ray_dtype)
+        rc = self.L.rtb200_multi_create_image(
+            self.h, C.byref(cp), flags, _addr(image), _addr(I_ang), C.byref(fc),
+            failed.ctypes.data_as(C.POINTER(abi.Ray)), abi.N_FAILED_MAX, C.byref(nf))
+        if rc < 0:
+            raise RTB200Error(rc, self.L.rtb200_multi_last_error(self.h).decode())
+        self.failure_code, self.n_failed = fc.value, nf.value
+        self.failed = failed[:min(nf.value, abi.N_FAILED_MAX)]
+        if rc == abi.RAYS_FAILED and raise_on_failed:
+            raise RaysFailed(fc.value, self.failed)
+        return image, I_ang
+
+    def timings(self):
+        t = (abi.Timings * self.n)()
+        ex, tot = C.c_float(0), C.c_float(0)
+        self.L.rtb200_multi_get_timings(self.h, t, C.byref(ex), C.byref(tot))
+        per = [{k: getattr(x, k) for k, _ in abi.Timings._fields_ if k != "reserved"} for x in t]
+        return {"per_device": per, "exchange_ms": ex.value, "total_ms": tot.value}

@@ -61,14 +61,14 @@ long long hostsim_march(const rtb200_problem *p, long long first, long long coun
         MarchResult res;
         unsigned steps = 0;
         if (flat) { // the flat state machine the GPU kernel runs
-            float zt[2 * RTB_N_SUB];
+            float zt[RTB_N_SUB];
             for (int iz = 0; iz < RTB_N_SUB; iz++)
-                march_sub_limits(zt, iz, P.dz0);
+                zt[iz] = march_sub_limit(iz, P.dz0);
             MarchConsts K;
-            march_consts(K, zt, P.N, P.method, P.c, P.use_emis != 0);
+            march_consts(K, P.lite, zt, P.N, P.method, P.c, P.use_emis != 0);
             FlatMarch fm;
-            flat_init(fm, P.lite, K, P.sxf[i], P.syf[j], P.tanA[k], P.tanB[m]);
-            while (flat_phase(fm) != PH_DONE && flat_iterate(fm, P.lite, K, sink)) {
+            flat_init(fm, K, P.sxf[i], P.syf[j], P.tanA[k], P.tanB[m]);
+            while (flat_phase(fm) != PH_DONE && flat_iterate(fm, K, sink)) {
             }
             res.pos = fm.pos;
             res.s = fm.s;

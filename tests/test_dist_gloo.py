@@ -58,7 +58,18 @@ def _worker(rank, world, port, nx_keep, out):
         sel2 = np.concatenate([rays[i, j] for j in rows_sel for i in range(e.nx)])
         r2 = pyoracle.Oracle().trace_rays(p, sel2, 1, 1.0)
         img2, ang2 = torch.from_numpy(r2["image"].copy()), torch.from_numpy(r2["I_ang"].copy())
+        # the gather form of the same exchange: every rank contributes its rows compactly
+        # (1/world of the image), the gathered blocks are un-permuted into the image
+        per = rdist.rows_per_rank(e.ny, world)
+        row_elems = e.nx * e.nv
+        part = torch.zeros(per * row_elems, dtype=torch.float64)
+        mine_rows = img2.view(e.ny, row_elems)[rank::world]
+        part.view(per, row_elems)[:mine_rows.shape[0]] = mine_rows
+        gathered = torch.empty(world * per * row_elems, dtype=torch.float64)
+        dist.all_gather_into_tensor(gathered, part)
+        img3 = rdist.unpermute_rows(gathered, torch.zeros_like(img2), e.ny, row_elems, world)
         rdist.exchange_rows(img2, ang2)
+        assert torch.equal(img3, img2)
         if rank == 0:
             np.save(out + "_image_cyclic.npy", img2.numpy())
         # seeded-style exchange: plain sums of full-size partials

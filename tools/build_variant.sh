@@ -9,5 +9,5 @@ mkdir -p "$ROOT/.variants"
 cd "$ROOT/raytrace-miniapp_b200/csrc"
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
      -Xcompiler -fPIC,-ffp-contract=off,-Wall -shared -cudart static "$@" \
-     -o "$ROOT/.variants/$NAME.so" rtb200_kernels.cu rtb200_host.cu rtb200_dat.cpp
+     -o "$ROOT/.variants/$NAME.so" rtb200_kernels.cu rtb200_host.cu rtb200_multi.cu rtb200_dat.cpp -ldl
 echo "$ROOT/.variants/$NAME.so"
