@@ -54,8 +54,6 @@ extern "C" {
  * returns. */
 #define RTB200_FLAG_LAZY_TABLES 0x2u
 
-/* Largest number of frequency bins the pixel-owner integration kernel covers in one pass. */
-#define RTB200_OWNER_K_MAX 128
 
 typedef struct rtb200_ray {
     float x, y, a, b;

@@ -132,7 +132,7 @@ struct rtb200_ctx {
     bool ieee_div = false; // never take the reciprocal-table division path (ddiv_by)
     int march_blocks = 0; // grid of the persistent march; 0 = resident CTAs x SMs (tuning override)
     unsigned long long *d_work = nullptr;
-    size_t handoff_bytes = (size_t) 4096 << 20; // B200 has 180 GB: one chunk for every shipped / synthetic size
+    size_t handoff_bytes = (size_t) 16384 << 20; // B200 has 180 GB: one chunk for every shipped / synthetic size (allocated to need)
 };
 
 namespace {
@@ -401,6 +401,7 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
     if (rc)
         return rc;
     Handoff h{ ctx->d_seg.p, ctx->d_meta.p, need_exit ? ctx->d_exit.p : nullptr, nullptr };
+    const bool owner = ctx->owner_ok && !out.Iv && !out.error;
     for (long long a = pix0; a < pix1; a += pix_per_chunk) {
         Chunk c;
         std::memset(&c, 0, sizeof(c));
@@ -415,7 +416,7 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
         if (rc)
             return rc;
         const size_t e1 = new_event(ctx, st);
-        if (ctx->owner_ok && !out.Iv && !out.error && P.K <= RTB200_OWNER_K_MAX) // one pass of <= 4 bin slots
+        if (owner)
             launch_integrate_ase_owner(P, c, h, out, st);
         else
             launch_integrate_scatter(P, c, false, h, out, st);
@@ -591,7 +592,7 @@ int rtb200_staged_info(const rtb200_ctx *ctx, rtb200_staged *out)
         return RTB200_ERR_ARG;
     const DevProblem &P = ctx->prob;
     out->method = P.method;
-    out->owner = ctx->owner_ok && P.K <= RTB200_OWNER_K_MAX ? 1 : 0;
+    out->owner = ctx->owner_ok ? 1 : 0;
     out->snx = P.snx;
     out->sny = P.sny;
     out->nx = P.nx;
@@ -635,7 +636,7 @@ static int launch_rows_impl(rtb200_ctx *ctx, int row_offset, int row_stride, dou
         return RTB200_ERR_ARG;
     }
     const DevProblem &P = ctx->prob;
-    if (compact && !(ctx->owner_ok && P.K <= RTB200_OWNER_K_MAX)) {
+    if (compact && !(ctx->owner_ok)) {
         ctx->err = "rtb200_launch_rows_compact: the staged problem is not traced by pixel owners "
                    "(rtb200_staged_info().owner == 0): use rtb200_launch_rows and a sum";
         return RTB200_ERR_ARG;

@@ -872,6 +872,110 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, RTB_OWNER_MINBLOCKS)
     }
 }
 
+// The same kernel for more than 128 frequency bins (spectral sweeps): the bins are covered in
+// tiles of 128 (four lane slots); per tile every ray of the pixel is integrated over the tile's
+// bins and the pixel's tile of the spectrum is written.  A ray's records are re-read once per
+// tile (they are small next to the lineshape rows, which are read exactly once).  I_ang gets one
+// atomic per (ray, tile).  A ray that fails (negative / NaN intensity) is reported by every tile
+// that sees it; the reference aborts on the first failure anyway (src/RayTraceImage.cpp:427-430).
+__global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, 3)
+    integrate_ase_owner_tiled_kernel(const DevProblem P, const Chunk c, const Handoff h, const Outputs o)
+{
+    constexpr int KS = 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double part[RTB_OWNER_WARPS][KS * 32];
+    __shared__ double exp_tab[64];
+    __shared__ uint4 rec_slab[RTB_OWNER_WARPS][32];
+    const float **s_gv = reinterpret_cast<const float **>(smem_raw); // [N] gv base pointers
+    for (int i = threadIdx.x; i < P.N; i += blockDim.x)
+        s_gv[i] = P.planes[i].gv;
+    load_exp_table(exp_tab); // includes __syncthreads()
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long p = phys_pixel(P, c, c.pix0 + blockIdx.x);
+    const PixelRays pr = pixel_rays(P, p);
+    const int S = (P.N - 1) * RTB_N_SUB;
+    const int K = P.K;
+    const long long slot0 = (long long) blockIdx.x * P.ab_max;
+    const PinnedConsts KC(P.kfp_g, exp_tab);
+    const unsigned slab_addr =
+        __shfl_sync(0xffffffffu, (unsigned) __cvta_generic_to_shared(&rec_slab[warp][0]), 0);
+    const int pi = __ldg(&P.pixI[pr.i]), pj = __ldg(&P.pixJ[pr.j]);
+    const bool store = o.compact || (pi >= 0 && pj >= 0);
+    const size_t opix = o.compact ? (size_t) (c.pix0 + blockIdx.x) : (size_t) pi + (size_t) pj * P.nx;
+    for (int kbase = 0; kbase < K; kbase += 32 * KS) {
+        double pix[KS], dv2[KS];
+        int koff[KS];
+#pragma unroll
+        for (int q = 0; q < KS; q++) {
+            pix[q] = 0.0;
+            const int k = kbase + lane + 32 * q;
+            dv2[q] = k < K ? __ldg(&P.dv2[k]) : 0.0;
+            const int live = K - kbase - 32 * q; // bins of this slot (see the one-pass kernel)
+            koff[q] = k < K ? k : (live > 0 ? kbase + 32 * q + (k - K) % live : K - 1);
+        }
+        for (int t0 = warp; t0 < pr.cnt; t0 += 32 * RTB_OWNER_WARPS) {
+            unsigned meta_l = RTB_META_INVALID;
+            int bin_l = -1;
+            {
+                const int t = t0 + lane * RTB_OWNER_WARPS;
+                if (t < pr.cnt) {
+                    meta_l = __ldg(&h.meta[slot0 + t]);
+                    const int ab = pr.ab0 + t * (int) P.n_parallel;
+                    const int ka = ab / P.snb, m = ab - ka * P.snb;
+                    const int ba = __ldg(&P.binA[ka]), bb = __ldg(&P.binB[m]);
+                    bin_l = (ba >= 0 && bb >= 0) ? ba + bb * P.na : -1;
+                }
+            }
+            const int n_here = min(32, (pr.cnt - t0 + RTB_OWNER_WARPS - 1) / RTB_OWNER_WARPS);
+            for (int j = 0; j < n_here; j++) {
+                const int t = t0 + j * RTB_OWNER_WARPS;
+                const long long slot = slot0 + t;
+                const unsigned meta = __shfl_sync(0xffffffffu, meta_l, j);
+                const int bin = __shfl_sync(0xffffffffu, bin_l, j);
+                if (meta & RTB_META_INVALID)
+                    continue; // error -1, reported by the march
+                double Iv[KS];
+#pragma unroll
+                for (int q = 0; q < KS; q++)
+                    Iv[q] = 0.0;
+                const int code = integrate_ray_ase_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, koff, Iv, KC,
+                                                            slab_addr);
+                if (code != 0) {
+                    if (lane == 0) {
+                        const int ab = pr.ab0 + t * (int) P.n_parallel;
+                        const int ka = ab / P.snb, m = ab % P.snb;
+                        report_failure(o.fail, code, P.sxf[pr.i], P.syf[pr.j], P.saf[ka], P.sbf[m]);
+                    }
+                    continue;
+                }
+                double w = 0.0;
+#pragma unroll
+                for (int q = 0; q < KS; q++) {
+                    w += dv2[q] * Iv[q];
+                    pix[q] += Iv[q] * P.scale;
+                }
+                w = warp_sum(w);
+                if (lane == 0 && bin >= 0)
+                    atomicAdd(&o.I_ang[bin], w);
+            }
+        }
+        __syncthreads(); // the previous tile's partials have been read
+#pragma unroll
+        for (int q = 0; q < KS; q++)
+            part[warp][q * 32 + lane] = pix[q];
+        __syncthreads();
+        if (store) {
+            for (int k = threadIdx.x; k < 32 * KS && kbase + k < K; k += blockDim.x) {
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < RTB_OWNER_WARPS; w++)
+                    sum += part[w][k];
+                o.image[(size_t) K * opix + kbase + k] = sum;
+            }
+        }
+    }
+}
+
 // One CTA per source row j: row j was traced by device j % world as its compact row j / world.
 __global__ void __launch_bounds__(256) unpermute_rows_kernel(const DevProblem P, const double *gathered, int world,
                                                              long long rows_per_dev, double *image)
@@ -912,7 +1016,8 @@ void launch_integrate_ase_owner(const DevProblem &P, const Chunk &c, const Hando
     case 1: integrate_ase_owner_kernel<1><<<blocks, threads, smem, st>>>(P, c, h, o); break;
     case 2: integrate_ase_owner_kernel<2><<<blocks, threads, smem, st>>>(P, c, h, o); break;
     case 3: integrate_ase_owner_kernel<3><<<blocks, threads, smem, st>>>(P, c, h, o); break;
-    default: integrate_ase_owner_kernel<4><<<blocks, threads, smem, st>>>(P, c, h, o); break;
+    case 4: integrate_ase_owner_kernel<4><<<blocks, threads, smem, st>>>(P, c, h, o); break;
+    default: integrate_ase_owner_tiled_kernel<<<blocks, threads, smem, st>>>(P, c, h, o); break; // K > 128
     }
 }
 

@@ -12,16 +12,48 @@
 //   * the owner cell of each source coordinate for method 1 (getIndex, RayTraceImageCPU.cpp:11-16);
 //   * the separable seed factors for method 2 (calc_seed_inline / interp_pchip, :168-247).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <thread>
+#include <vector>
 
 #include "../../include/rtb200.h"
 #include "rtb200_device.cuh"
 
 namespace rtb {
+
+// Splits [0, n) into at most 8 contiguous pieces and runs fn(piece, begin, end) on host threads
+// when the job is large enough to pay for them (re-layout of multi-megabyte gain planes); small
+// problems - every shipped input - stay on the calling thread (one piece).
+enum { RTB_MAX_PIECES = 8 };
+template <class F>
+inline void parallel_pieces(size_t n, size_t bytes, F fn)
+{
+    unsigned t = 1;
+    if (bytes >= ((size_t) 8 << 20)) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        t = hw > RTB_MAX_PIECES ? (unsigned) RTB_MAX_PIECES : (hw < 1 ? 1 : hw);
+        if ((size_t) t > n)
+            t = (unsigned) (n ? n : 1);
+    }
+    if (t <= 1) {
+        fn(0u, (size_t) 0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = (n + t - 1) / t;
+    for (unsigned i = 0; i < t; i++) {
+        const size_t a = std::min(n, i * per), b = std::min(n, a + per);
+        if (a < b)
+            th.emplace_back([=]() { fn(i, a, b); });
+    }
+    for (auto &x : th)
+        x.join();
+}
 
 // findfirstsingle (RayTraceImageHelper.h:101-117)
 inline size_t host_findfirstsingle(const double *X, size_t n, double Y)
@@ -175,9 +207,13 @@ inline void fill_cell_records(const rtb200_gain_plane &g, const AxisCell *cx, co
                               CellRec *t)
 {
     const int Nx = g.Nx, Ny = g.Ny;
-    std::memset(t, 0, sizeof(CellRec) * (size_t) Nx * Ny);
-    for (int j = 0; j + 1 < Ny; j++)
-        for (int i = 0; i + 1 < Nx; i++) {
+    parallel_pieces((size_t) Ny, sizeof(CellRec) * (size_t) Nx * Ny, [=](unsigned, size_t j0, size_t j1) {
+    for (int j = (int) j0; j < (int) j1; j++)
+        for (int i = 0; i < Nx; i++) {
+            if (i + 1 >= Nx || j + 1 >= Ny) { // last row / column: never addressed
+                std::memset(&t[(size_t) i + (size_t) j * Nx], 0, sizeof(CellRec));
+                continue;
+            }
             const size_t i1 = (size_t) i + (size_t) j * Nx;
             const size_t c[4] = { i1, i1 + 1, i1 + (size_t) Nx, i1 + (size_t) Nx + 1 };
             CellRec r;
@@ -198,6 +234,33 @@ inline void fill_cell_records(const rtb200_gain_plane &g, const AxisCell *cx, co
             r.rdy = cy[j + 1].rd;
             t[i1] = r;
         }
+    });
+}
+
+// max over |v| as float bit patterns (sign cleared; NaN > inf > every finite value)
+inline unsigned abs_max_bits(const float *v, size_t n, unsigned m = 0u)
+{
+    const uint32_t *b = reinterpret_cast<const uint32_t *>(v);
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t a = b[i] & 0x7fffffffu;
+        m = a > m ? a : m;
+    }
+    return m;
+}
+
+// Copies n floats and returns max |v| as float bits (sign cleared; NaN > inf > every finite
+// value), on host threads for large tables.
+inline unsigned copy_abs_max(float *dst, const float *src, size_t n, unsigned m0)
+{
+    unsigned part[RTB_MAX_PIECES] = { 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u };
+    parallel_pieces(n, n * sizeof(float), [&part, dst, src](unsigned piece, size_t a, size_t b) {
+        std::memcpy(dst + a, src + a, (b - a) * sizeof(float));
+        part[piece] = abs_max_bits(src + a, b - a);
+    });
+    unsigned m = m0;
+    for (unsigned v : part)
+        m = v > m ? v : m;
+    return m;
 }
 
 // Bump allocator over the staging blob.  With host == nullptr it only measures.
@@ -232,17 +295,6 @@ struct GvBlob {
     bool copy;
     size_t bytes;
 };
-
-// max over |v| as float bit patterns (sign cleared; NaN > inf > every finite value)
-inline unsigned abs_max_bits(const float *v, size_t n, unsigned m = 0u)
-{
-    const uint32_t *b = reinterpret_cast<const uint32_t *>(v);
-    for (size_t i = 0; i < n; i++) {
-        const uint32_t a = b[i] & 0x7fffffffu;
-        m = a > m ? a : m;
-    }
-    return m;
-}
 
 // Packs `p` into the blob.  Returns the number of bytes used; fills `out` (pointers relative
 // to dev_base).  explicit_rays: the ray list comes separately (rtb200_trace_rays), so only the
@@ -314,14 +366,15 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
             P.fast_div = ok ? 1 : 0;
             std::memcpy(x, g.x, sizeof(double) * g.Nx);
             std::memcpy(y, g.y, sizeof(double) * g.Ny);
-            for (size_t q = 0; q < nn; q++) {
-                node[q].n = g.n[q];
-                node[q].g0 = g.g0[q];
-                node[q].E0 = g.E0 ? g.E0[q] : 0.0f;
-            }
+            parallel_pieces(nn, nn * sizeof(Node), [&](unsigned, size_t q0, size_t q1) {
+                for (size_t q = q0; q < q1; q++) {
+                    node[q].n = g.n[q];
+                    node[q].g0 = g.g0[q];
+                    node[q].E0 = g.E0 ? g.E0[q] : 0.0f;
+                }
+            });
             if (gv && (!gvb || gvb->copy)) {
-                std::memcpy(gv, g.gv, sizeof(float) * nn * (size_t) K);
-                gv_absmax = abs_max_bits(g.gv, nn * (size_t) K, gv_absmax);
+                gv_absmax = copy_abs_max(gv, g.gv, nn * (size_t) K, gv_absmax);
             } else {
                 gv_absmax = 0x7fffffffu; // tables filled later: pack_gv() returns the value
             }
@@ -500,8 +553,7 @@ inline unsigned pack_gv(const rtb200_problem &p, char *host)
         const size_t n = (size_t) g.Nx * g.Ny * (size_t) K;
         const float *unused;
         float *gv = gv_blob.alloc<float>(n, &unused);
-        std::memcpy(gv, g.gv, sizeof(float) * n);
-        m = abs_max_bits(g.gv, n, m);
+        m = copy_abs_max(gv, g.gv, n, m);
     }
     return m;
 }

@@ -57,6 +57,20 @@ def ase_medium_synth(small, rows_factor=1):
     return Problem(euv, planes, None, None, 0, 1)
 
 
+def seed_medium_synth(small):
+    """seed_medium stand-in (BASELINE.json config 2; seed_medium.dat is not in the reference
+    checkout, .MISSING_LARGE_BLOBS:2): seed_small with BOTH beams refined as `-scale=8` does
+    (scale_problem, src/CreateImageHelpers.cpp:144-150: euv_beam and seed_beam x 8^0.25 per
+    axis -> seed grid 201 x 42 x 85 x 85 = 60 994 350 rays) and N raised from 3 to 6 with the
+    same linear blends of gain[1], gain[2] as ase_medium_synth.  The seed profile is unchanged."""
+    f = 8.0 ** 0.25
+    euv = scale_beam(small.euv_beam, f)
+    sb = scale_beam(small.seed_beam, f)
+    g = small.gain
+    planes = [g[0]] + [blend_planes(g[1], g[2], w) for w in (0.0, 0.25, 0.5, 0.75, 1.0)]
+    return Problem(euv, planes, sb, small.seed, 0, 1)
+
+
 def resample_gain(g, fx, fy):
     """Bilinear resampling of a gain plane to fx x fy finer cells (S4 family, config 4)."""
     Nx, Ny = (g.Nx - 1) * fx + 1, (g.Ny - 1) * fy + 1
