@@ -260,6 +260,23 @@ int rtb200_parse_dat(const void *bytes, size_t n_bytes, rtb200_problem **problem
                      const double **golden_image, const double **golden_I_ang);
 void rtb200_free_problem(rtb200_problem *problem);
 
+/* RayTrace::create_image straight from the serialized form (what the reference's driver does
+ * with loadInput + create_image, src/CreateImage.cpp:26-58, :147-152): the large arrays of every
+ * gain plane are read ONCE, from the (unaligned) byte stream into the pinned staging blob, and
+ * uploaded - file buffer -> pinned blob -> device, no intermediate AoS-of-pointers copy
+ * (create_image_struct::unpack, src/RayTraceStructures.cpp:2224-2292).  `bytes` is the payload
+ * after the file's uint64 length and must stay valid during the call. */
+int rtb200_create_image_from_dat(rtb200_ctx *ctx, const void *bytes, size_t n_bytes, unsigned flags,
+                                 double *image, double *I_ang, unsigned *failure_code,
+                                 rtb200_ray *failed, int max_failed, int *n_failed);
+
+/* create_image_struct::pack (src/RayTraceStructures.cpp:2159-2223): serializes a problem (plus
+ * optional golden arrays) into the payload of a .dat file that the reference's own CreateImage
+ * loads.  Fields off the image-formation path get neutral values (one z plane, v = 0, no seed
+ * shapes, gv0 = 0).  out == NULL only measures; *n_bytes always receives the size needed. */
+int rtb200_write_dat(const rtb200_problem *problem, const double *golden_image,
+                     const double *golden_I_ang, void *out, size_t capacity, size_t *n_bytes);
+
 /* ---- measurement helpers ---------------------------------------------------------------------- */
 
 /* DFMA micro-benchmark: returns the measured FP64 instruction rate (warp-level FMA

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Writes patched COPIES of the two reference files a maintainer touches to register the B200
 back-end into the git-ignored build directory oracle/_ref/patched/:
-  src/RayTraceImage.cpp  one extern block and two `else if` branches next to the "cuda" ones
-                         (:47-75, :389-405);
+  src/RayTraceImage.cpp  one extern block, two `else if` branches next to the "cuda" ones
+                         (:47-75, :389-405) and the two direct entries ("b200-direct",
+                         "b200-multigpu") ahead of the host ray list (:277);
   src/CreateImage.cpp    the method name in the driver's default list and GPU warm-up (:90-132).
 Nothing else of the reference is touched; the copies never enter the repository.  See
 INTEGRATION.md for the same change as a diff."""
@@ -33,6 +34,7 @@ extern void RayTraceImageB200Loop( int N, const RayTrace::EUV_beam_struct& euv_b
     std::vector<ray_struct> &failed_rays );
 extern void RayTraceImageB200SetDevice( int device );
 extern void RayTraceImageB200Direct( const RayTrace::create_image_struct *info, double *image, double *I_ang );
+extern void RayTraceImageB200MultiDirect( const RayTrace::create_image_struct *info, double *image, double *I_ang );
 extern "C" int rtb200_device_count( void );
 '''
 anchor = "/**********************************************************************\n* Call RayTraceImage function from a thread loop"
@@ -41,7 +43,7 @@ s = s.replace(anchor, extern + "\n" + anchor)
 branch = '''    } else if ( compute_method == "b200" ) {
         RayTraceImageB200Loop( N, std::ref(*info->euv_beam), info->gain, info->seed,
             method, rays, scale, image, I_ang, failure_code, failed_rays );
-    } else if ( compute_method == "b200-multigpu" ) {
+    } else if ( compute_method == "b200-threadloop" ) {
         RayTraceImageThreadLoop( rtb200_device_count(), RayTraceImageB200Loop, RayTraceImageB200SetDevice,
             N, std::ref(*info->euv_beam), info->gain, info->seed,
             method, rays, scale, image, I_ang, failure_code, failed_rays );
@@ -52,6 +54,11 @@ direct = '''    {
         std::transform( m2.begin(), m2.end(), m2.begin(), ::tolower );
         if ( m2 == "b200-direct" ) {
             RayTraceImageB200Direct( info, image, I_ang );
+            PROFILE_STOP( "create_image" );
+            return;
+        }
+        if ( m2 == "b200-multigpu" ) {
+            RayTraceImageB200MultiDirect( info, image, I_ang );
             PROFILE_STOP( "create_image" );
             return;
         }

@@ -750,6 +750,29 @@ int rtb200_create_image(rtb200_ctx *ctx, const rtb200_problem *problem, unsigned
     return finish(ctx, failure_code, failed, max_failed, n_failed);
 }
 
+extern "C" int rtb200_parse_dat_view(const void *bytes, size_t n_bytes, rtb200_problem **problem);
+
+int rtb200_create_image_from_dat(rtb200_ctx *ctx, const void *bytes, size_t n_bytes, unsigned flags,
+                                 double *image, double *I_ang, unsigned *failure_code,
+                                 rtb200_ray *failed, int max_failed, int *n_failed)
+{
+    if (!ctx || !bytes) {
+        if (ctx)
+            ctx->err = "rtb200_create_image_from_dat: NULL argument";
+        return RTB200_ERR_ARG;
+    }
+    rtb200_problem *p = nullptr;
+    int rc = rtb200_parse_dat_view(bytes, n_bytes, &p);
+    if (rc != RTB200_OK) {
+        ctx->err = "malformed .dat byte stream";
+        return rc;
+    }
+    // the large arrays of `p` alias `bytes`: the packer reads them once, into the pinned blob
+    rc = rtb200_create_image(ctx, p, flags, image, I_ang, failure_code, failed, max_failed, n_failed);
+    rtb200_free_problem(p);
+    return rc;
+}
+
 namespace {
 
 // tanf(1e-3f*a) per ray through a small open-addressing cache keyed by the float's bits: ray

@@ -767,6 +767,48 @@ __device__ __forceinline__ int integrate_ray_gain_fast(const DevProblem &P, cons
     return any_neg ? 2 : (any_nan ? 3 : 0);
 }
 
+// The same integrator for records that are ALREADY parked in the warp's slab (entries lo..hi-1 of
+// this ray: {(double) gvl, lineshape row address}): the scatter kernel fetches the records of a
+// whole batch of rays with coalesced loads before it walks the batch, so the DRAM latency of the
+// hand-off records is paid once per batch instead of once per ray.
+#define RTB_SLAB_RECORDS 256 // per warp
+template <int KS>
+__device__ __forceinline__ int integrate_ray_gain_slab(const DevProblem &P, unsigned meta, int lane, int kbase,
+                                                       double (&Iv)[KS], const ArrayConsts &KC, unsigned slab)
+{
+    const int lo = meta & 0xfff, hi = (meta >> 12) & 0xfff;
+    const int K = P.K;
+    int koff[KS];
+    double gl[KS];
+#pragma unroll
+    for (int q = 0; q < KS; q++) {
+        koff[q] = min(kbase + lane + 32 * q, K - 1);
+        gl[q] = 0.0;
+    }
+    for (int j = lo; j < hi; j++) {
+        uint4 e;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
+                     : "r"(slab + 16u * (unsigned) j));
+        // a record with gvl == 0 adds exactly +0 to every bin: fma(0, gv, gl) == gl
+        const double gvl = __longlong_as_double((long long) (((unsigned long long) e.y << 32) | e.x));
+        const float *row = reinterpret_cast<const float *>(((unsigned long long) e.w << 32) | e.z);
+#pragma unroll
+        for (int q = 0; q < KS; q++)
+            gl[q] = __fma_rn(gvl, (double) __ldg(row + koff[q]), gl[q]);
+    }
+    bool neg = false, nan = false;
+#pragma unroll
+    for (int q = 0; q < KS; q++) {
+        Iv[q] *= exp_any(gl[q], KC);
+        neg = neg || Iv[q] < 0.0;
+        nan = nan || Iv[q] != Iv[q];
+    }
+    const bool any_neg = __any_sync(0xffffffffu, neg);
+    const bool any_nan = __any_sync(0xffffffffu, nan);
+    return any_neg ? 2 : (any_nan ? 3 : 0);
+}
+
 #define RTB_OWNER_WARPS 8
 #ifndef RTB_OWNER_MINBLOCKS
 #define RTB_OWNER_MINBLOCKS 4
@@ -1132,8 +1174,10 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double exp_tab[64];
-    __shared__ uint4 rec_slab[8][32]; // per-warp record + row-address slab (256 threads)
-    const float **s_gv = reinterpret_cast<const float **>(smem_raw); // [N] gv base pointers
+    // dynamic shared memory: per-warp record + row-address slabs (8 x RTB_SLAB_RECORDS x 16 B),
+    // then the gv base pointers of the planes
+    uint4 *rec_slab = reinterpret_cast<uint4 *>(smem_raw);
+    const float **s_gv = reinterpret_cast<const float **>(smem_raw + 8 * RTB_SLAB_RECORDS * sizeof(uint4)); // [N]
     for (int i = threadIdx.x; i < P.N; i += blockDim.x)
         s_gv[i] = P.planes[i].gv;
     load_exp_table(exp_tab); // includes __syncthreads()
@@ -1141,7 +1185,7 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
     const bool gain_only = P.use_emis == 0;
     const int lane = threadIdx.x & 31;
     const unsigned slab =
-        __shfl_sync(0xffffffffu, (unsigned) __cvta_generic_to_shared(&rec_slab[threadIdx.x >> 5][0]), 0);
+        __shfl_sync(0xffffffffu, (unsigned) __cvta_generic_to_shared(rec_slab + (threadIdx.x >> 5) * RTB_SLAB_RECORDS), 0);
     // slot counts of one chunk fit 32 bits (the host sizes chunks that way): 32-bit loop counters
     const int warp_id = (int) ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int n_warps = (int) ((gridDim.x * blockDim.x) >> 5);
@@ -1255,6 +1299,11 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
                 bin = i3 + i4 * P.na;
         }
     };
+    // Rays whose records are fetched together (gain-only integration): as many as fit the slab.
+    int batch = 32;
+    while (batch > 1 && batch * S > RTB_SLAB_RECORDS)
+        batch >>= 1;
+    const bool batched = gain_only && S >= 1 && S <= RTB_SLAB_RECORDS;
     const int n_runs = (n_slots + RUN - 1) / RUN;
     for (int run = warp_id; run < n_runs; run += n_warps) {
     const int slot_end = min((run + 1) * RUN, n_slots);
@@ -1272,6 +1321,27 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
     const int n_here = min(slot_end - base, 32);
     for (int j = 0; j < n_here; j++) {
         const long long slot = base + j; // 64-bit where it scales addresses
+        if (batched && (j & (batch - 1)) == 0) {
+            // one coalesced sweep over the records of the next `batch` rays (they are contiguous
+            // in the hand-off arena); entries outside a ray's visited range are never read
+            __syncwarp();
+            const int nrec = min(batch, n_here - j) * S;
+            const SegRec *src = h.seg + slot * S;
+            for (int r = lane; r < nrec; r += 32) {
+                const int4 rv = __ldg(reinterpret_cast<const int4 *>(&src[r]));
+                const int sg = r % S;
+                const float *row = s_gv[sg / RTB_N_SUB + 1] + (size_t) rv.z * K;
+                const unsigned long long ra = reinterpret_cast<unsigned long long>(row);
+                const unsigned long long gd =
+                    (unsigned long long) __double_as_longlong((double) __int_as_float(rv.x));
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slab + 16u * (unsigned) r),
+                             "r"((unsigned) gd), "r"((unsigned) (gd >> 32)), "r"((unsigned) ra),
+                             "r"((unsigned) (ra >> 32))
+                             : "memory");
+            }
+            __syncwarp();
+        }
+        const unsigned ray_slab = slab + 16u * (unsigned) ((j & (batch - 1)) * S);
         const unsigned meta = __shfl_sync(0xffffffffu, meta_l, j);
         if (meta & RTB_META_INACTIVE)
             continue;
@@ -1292,7 +1362,8 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
                 Iv[q] = (f != 0.0 && k < K) ? __dmul_rn(f, __ldg(&P.seed_fv[k])) : 0.0;
             }
             if (!invalid) {
-                const int cc = gain_only
+                const int cc = batched ? integrate_ray_gain_slab<KS>(P, meta, lane, kbase, Iv, KC, ray_slab)
+                               : gain_only
                                    ? integrate_ray_gain_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, kbase, Iv, KC, slab)
                                    : integrate_ray<KS>(P, h.seg + slot * S, meta, lane, kbase, Iv, exp_tab);
                 if (cc != 0) {
@@ -1335,7 +1406,9 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
                     const int k = kbase + lane + 32 * q;
                     Iv[q] = (f != 0.0 && k < K) ? __dmul_rn(f, __ldg(&P.seed_fv[k])) : 0.0;
                 }
-                if (gain_only)
+                if (batched)
+                    integrate_ray_gain_slab<KS>(P, meta, lane, kbase, Iv, KC, ray_slab);
+                else if (gain_only)
                     integrate_ray_gain_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, kbase, Iv, KC, slab);
                 else
                     integrate_ray<KS>(P, h.seg + slot * S, meta, lane, kbase, Iv, exp_tab);
@@ -1489,7 +1562,7 @@ void launch_integrate_scatter(const DevProblem &P, const Chunk &c, bool list_mod
     if (blocks > cap)
         blocks = cap;
     const int ks = std::min(4, (P.K + 31) / 32);
-    const size_t smem = sizeof(float *) * (size_t) P.N;
+    const size_t smem = 8 * RTB_SLAB_RECORDS * sizeof(uint4) + sizeof(float *) * (size_t) P.N;
 #define RTB_LAUNCH_SCATTER(KS_)                                                                  \
     do {                                                                                         \
         if (list_mode)                                                                           \

@@ -26,6 +26,16 @@
 
 namespace rtb {
 
+// The large arrays of a problem (n, g0, E0, gv) may alias an unaligned byte stream
+// (rtb200_create_image_from_dat): every read of them goes through memcpy.
+template <class T>
+inline T ld_u(const T *p)
+{
+    T v;
+    std::memcpy(&v, p, sizeof(T));
+    return v;
+}
+
 // Splits [0, n) into at most 8 contiguous pieces and runs fn(piece, begin, end) on host threads
 // when the job is large enough to pay for them (re-layout of multi-megabyte gain planes); small
 // problems - every shipped input - stay on the calling thread (one piece).
@@ -217,15 +227,17 @@ inline void fill_cell_records(const rtb200_gain_plane &g, const AxisCell *cx, co
             const size_t i1 = (size_t) i + (size_t) j * Nx;
             const size_t c[4] = { i1, i1 + 1, i1 + (size_t) Nx, i1 + (size_t) Nx + 1 };
             CellRec r;
+            double nc[4];
             for (int q = 0; q < 4; q++) {
-                r.nf[q] = (float) g.n[c[q]];
-                r.g0[q] = g.g0[c[q]];
-                r.E0[q] = g.E0 ? g.E0[c[q]] : 0.0f;
+                nc[q] = ld_u(&g.n[c[q]]);
+                r.nf[q] = (float) nc[q];
+                r.g0[q] = ld_u(&g.g0[c[q]]);
+                r.E0[q] = g.E0 ? ld_u(&g.E0[c[q]]) : 0.0f;
             }
-            r.n10 = g.n[c[1]] - g.n[c[0]];
-            r.n32 = g.n[c[3]] - g.n[c[2]];
-            r.n20 = g.n[c[2]] - g.n[c[0]];
-            r.n31 = g.n[c[3]] - g.n[c[1]];
+            r.n10 = nc[1] - nc[0];
+            r.n32 = nc[3] - nc[2];
+            r.n20 = nc[2] - nc[0];
+            r.n31 = nc[3] - nc[1];
             r.xl = cx[i + 1].lo;
             r.dxd = cx[i + 1].dd;
             r.rdx = cx[i + 1].rd;
@@ -240,9 +252,11 @@ inline void fill_cell_records(const rtb200_gain_plane &g, const AxisCell *cx, co
 // max over |v| as float bit patterns (sign cleared; NaN > inf > every finite value)
 inline unsigned abs_max_bits(const float *v, size_t n, unsigned m = 0u)
 {
-    const uint32_t *b = reinterpret_cast<const uint32_t *>(v);
+    const unsigned char *b = reinterpret_cast<const unsigned char *>(v);
     for (size_t i = 0; i < n; i++) {
-        const uint32_t a = b[i] & 0x7fffffffu;
+        uint32_t a;
+        std::memcpy(&a, b + 4 * i, 4);
+        a &= 0x7fffffffu;
         m = a > m ? a : m;
     }
     return m;
@@ -368,9 +382,9 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
             std::memcpy(y, g.y, sizeof(double) * g.Ny);
             parallel_pieces(nn, nn * sizeof(Node), [&](unsigned, size_t q0, size_t q1) {
                 for (size_t q = q0; q < q1; q++) {
-                    node[q].n = g.n[q];
-                    node[q].g0 = g.g0[q];
-                    node[q].E0 = g.E0 ? g.E0[q] : 0.0f;
+                    node[q].n = ld_u(&g.n[q]);
+                    node[q].g0 = ld_u(&g.g0[q]);
+                    node[q].E0 = g.E0 ? ld_u(&g.E0[q]) : 0.0f;
                 }
             });
             if (gv && (!gvb || gvb->copy)) {

@@ -196,62 +196,68 @@ void RayTraceImageB200Loop(int N, const RayTrace::EUV_beam_struct &beam,
 }
 
 
-// The full-speed entry: called by create_image BEFORE it builds the host ray list
-// (src/RayTraceImage.cpp:277), method name "b200-direct".  The problem descriptor carries the
-// grids and N_start / N_parallel, so the rays are enumerated on the device, ASE pixels are
-// owned by thread blocks and the seed is tabulated per grid index (rtb200_create_image).
-// image / I_ang are the zeroed buffers create_image allocated (:271-274); failures are
-// reported the way create_image does (:427-430): messages on stderr, then exit(-1).
-void RayTraceImageB200Direct(const RayTrace::create_image_struct *info, double *image, double *I_ang)
-{
-    auto fill = [](rtb200_beam &b, int nx, int ny, int na, int nb, double dx, double dy, double da,
-                   double db, const double *x, const double *y, const double *a, const double *bb) {
-        memset(&b, 0, sizeof(b));
-        b.nx = nx, b.ny = ny, b.na = na, b.nb = nb;
-        b.dx = dx, b.dy = dy, b.da = da, b.db = db;
-        b.x = x, b.y = y, b.a = a, b.b = bb;
-    };
-    const RayTrace::EUV_beam_struct &e = *info->euv_beam;
+// ---- the full-speed entries: called by create_image BEFORE it builds the host ray list --------
+// (src/RayTraceImage.cpp:277), method names "b200-direct" and "b200-multigpu".  The problem
+// descriptor carries the grids and N_start / N_parallel, so the rays are enumerated on the
+// device, ASE pixels are owned by thread blocks and the seed is tabulated per grid index
+// (rtb200_create_image).  image / I_ang are the zeroed buffers create_image allocated
+// (:271-274); failures are reported the way create_image does (:427-430): messages on stderr,
+// then exit(-1).
+namespace {
+
+struct ProblemView { // POD descriptors of include/rtb200.h filled from the reference's structs (pointers only)
     rtb200_beam euv, sbeam;
-    fill(euv, e.nx, e.ny, e.na, e.nb, e.dx, e.dy, e.da, e.db, e.x, e.y, e.a, e.b);
-    euv.nv = e.nv;
-    euv.dz = e.dz;
-    euv.dv = e.dv;
-    if (info->seed_beam) {
-        const RayTrace::seed_beam_struct &s = *info->seed_beam;
-        fill(sbeam, s.nx, s.ny, s.na, s.nb, s.dx, s.dy, s.da, s.db, s.x, s.y, s.a, s.b);
-    }
-    std::vector<rtb200_gain_plane> planes(info->N);
-    for (int i = 0; i < info->N; i++) {
-        const RayTrace::ray_gain_struct &g = info->gain[i];
-        planes[i].Nx = g.Nx, planes[i].Ny = g.Ny, planes[i].Nv = g.Nv;
-        planes[i].x = g.x, planes[i].y = g.y, planes[i].n = g.n;
-        planes[i].g0 = g.g0, planes[i].E0 = g.E0, planes[i].gv = g.gv;
-    }
+    std::vector<rtb200_gain_plane> planes;
     rtb200_seed sd;
-    if (info->seed) {
-        for (int i = 0; i < 5; i++) {
-            sd.dim[i] = info->seed->dim[i];
-            sd.x[i] = info->seed->x[i];
-            sd.f[i] = info->seed->f[i];
-        }
-        sd.f0 = info->seed->f0;
-    }
     rtb200_problem prob;
-    memset(&prob, 0, sizeof(prob));
-    prob.N = info->N;
-    prob.N_start = info->N_start;
-    prob.N_parallel = info->N_parallel;
-    prob.euv_beam = &euv;
-    prob.seed_beam = info->seed_beam ? &sbeam : nullptr;
-    prob.gain = planes.data();
-    prob.seed = info->seed ? &sd : nullptr;
-    rtb200_ctx *ctx = context();
-    unsigned failure_code = 0;
-    int n_failed = 0;
-    const int rc = rtb200_create_image(ctx, &prob, 0, image, I_ang, &failure_code, nullptr, 0, &n_failed);
+    explicit ProblemView(const RayTrace::create_image_struct *info)
+    {
+        auto fill = [](rtb200_beam &b, int nx, int ny, int na, int nb, double dx, double dy, double da,
+                       double db, const double *x, const double *y, const double *a, const double *bb) {
+            memset(&b, 0, sizeof(b));
+            b.nx = nx, b.ny = ny, b.na = na, b.nb = nb;
+            b.dx = dx, b.dy = dy, b.da = da, b.db = db;
+            b.x = x, b.y = y, b.a = a, b.b = bb;
+        };
+        const RayTrace::EUV_beam_struct &e = *info->euv_beam;
+        fill(euv, e.nx, e.ny, e.na, e.nb, e.dx, e.dy, e.da, e.db, e.x, e.y, e.a, e.b);
+        euv.nv = e.nv;
+        euv.dz = e.dz;
+        euv.dv = e.dv;
+        if (info->seed_beam) {
+            const RayTrace::seed_beam_struct &s = *info->seed_beam;
+            fill(sbeam, s.nx, s.ny, s.na, s.nb, s.dx, s.dy, s.da, s.db, s.x, s.y, s.a, s.b);
+        }
+        planes.resize(info->N);
+        for (int i = 0; i < info->N; i++) {
+            const RayTrace::ray_gain_struct &g = info->gain[i];
+            planes[i].Nx = g.Nx, planes[i].Ny = g.Ny, planes[i].Nv = g.Nv;
+            planes[i].x = g.x, planes[i].y = g.y, planes[i].n = g.n;
+            planes[i].g0 = g.g0, planes[i].E0 = g.E0, planes[i].gv = g.gv;
+        }
+        if (info->seed) {
+            for (int i = 0; i < 5; i++) {
+                sd.dim[i] = info->seed->dim[i];
+                sd.x[i] = info->seed->x[i];
+                sd.f[i] = info->seed->f[i];
+            }
+            sd.f0 = info->seed->f0;
+        }
+        memset(&prob, 0, sizeof(prob));
+        prob.N = info->N;
+        prob.N_start = info->N_start;
+        prob.N_parallel = info->N_parallel;
+        prob.euv_beam = &euv;
+        prob.seed_beam = info->seed_beam ? &sbeam : nullptr;
+        prob.gain = planes.data();
+        prob.seed = info->seed ? &sd : nullptr;
+    }
+};
+
+void report(int rc, const char *msg, unsigned failure_code)
+{
     if (rc < 0) {
-        fprintf(stderr, "rtb200 error %d: %s\n", rc, rtb200_last_error(ctx));
+        fprintf(stderr, "rtb200 error %d: %s\n", rc, msg);
         exit(-1);
     }
     if (failure_code != 0) {
@@ -264,4 +270,43 @@ void RayTraceImageB200Direct(const RayTrace::create_image_struct *info, double *
         fprintf(stderr, "Some rays failed\n");
         exit(-1);
     }
+}
+
+} // namespace
+
+void RayTraceImageB200Direct(const RayTrace::create_image_struct *info, double *image, double *I_ang)
+{
+    ProblemView v(info);
+    rtb200_ctx *ctx = context();
+    unsigned failure_code = 0;
+    int n_failed = 0;
+    const int rc = rtb200_create_image(ctx, &v.prob, 0, image, I_ang, &failure_code, nullptr, 0, &n_failed);
+    report(rc, rtb200_last_error(ctx), failure_code);
+}
+
+// "b200-multigpu": every device of the box (or RTB200_NGPU of them) in one call.  Replaces the
+// reference's cuda-multigpu branch (src/RayTraceImage.cpp:396-405: ThreadLoop over contiguous
+// chunks of a host ray list, host-side sum, and - through the cudaSetDevice in the parent thread,
+// :116-119 - every worker on device 0) by rtb200_multi_create_image: rows sharded row-cyclically,
+// partial results exchanged over NVLink by NCCL, one download.  The communicator is created at the
+// first call and kept (ncclCommInitAll takes about a second).
+void RayTraceImageB200MultiDirect(const RayTrace::create_image_struct *info, double *image, double *I_ang)
+{
+    static std::mutex mtx;
+    static rtb200_multi *multi = nullptr;
+    std::lock_guard<std::mutex> lock(mtx);
+    if (!multi) {
+        int n = rtb200_device_count();
+        if (const char *e = getenv("RTB200_NGPU"))
+            n = atoi(e) < n ? atoi(e) : n;
+        if (n < 1 || rtb200_multi_create(nullptr, n, &multi) != RTB200_OK) {
+            fprintf(stderr, "rtb200: cannot set up %d device(s): %s\n", n, rtb200_multi_last_error(multi));
+            exit(-1);
+        }
+    }
+    ProblemView v(info);
+    unsigned failure_code = 0;
+    int n_failed = 0;
+    const int rc = rtb200_multi_create_image(multi, &v.prob, 0, image, I_ang, &failure_code, nullptr, 0, &n_failed);
+    report(rc, rtb200_multi_last_error(multi), failure_code);
 }

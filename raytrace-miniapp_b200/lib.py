@@ -98,6 +98,10 @@ def load():
                                    P(abi.c_double_p), P(abi.c_double_p)]
     L.rtb200_free_problem.argtypes = [P(abi.CProblem)]
     L.rtb200_free_problem.restype = None
+    L.rtb200_write_dat.argtypes = [P(abi.CProblem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                   P(C.c_size_t)]
+    L.rtb200_create_image_from_dat.argtypes = [ctx, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p,
+                                               C.c_void_p, P(C.c_uint), P(abi.Ray), C.c_int, P(C.c_int)]
     L.rtb200_measure_fp64_peak.argtypes = [ctx, P(C.c_double)]
     L.rtb200_check_fdiv.argtypes = [ctx, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, P(C.c_ulonglong),
                                     P(C.c_float), P(C.c_float)]
@@ -107,6 +111,24 @@ def load():
 
 def device_count():
     return load().rtb200_device_count()
+
+
+def write_dat_payload(problem, image=None, I_ang=None):
+    """rtb200_write_dat (the C++ writer of the reference's wire format): the payload of a .dat
+    file as bytes; a file is struct.pack("<Q", len(payload)) + payload."""
+    L = load()
+    cp, keep = problem.c_struct()
+    img = None if image is None else np.ascontiguousarray(image, np.float64)
+    ang = None if I_ang is None else np.ascontiguousarray(I_ang, np.float64)
+    n = C.c_size_t(0)
+    rc = L.rtb200_write_dat(C.byref(cp), _addr(img), _addr(ang), None, 0, C.byref(n))
+    if rc != abi.OK:
+        raise RTB200Error(rc, "rtb200_write_dat")
+    buf = np.empty(n.value, np.uint8)
+    rc = L.rtb200_write_dat(C.byref(cp), _addr(img), _addr(ang), buf.ctypes.data, buf.size, C.byref(n))
+    if rc != abi.OK:
+        raise RTB200Error(rc, "rtb200_write_dat")
+    return buf.tobytes()
 
 
 def _check_out(a, n, name):
@@ -180,6 +202,21 @@ class Context:
         self.failed = failed[:min(nf.value, abi.N_FAILED_MAX)]
         if rc == abi.RAYS_FAILED and raise_on_failed:
             raise RaysFailed(fc.value, self.failed)
+        return image, I_ang
+
+    def create_image_from_dat(self, payload, n_image, n_ang, flags=0, raise_on_failed=True):
+        """rtb200_create_image_from_dat: the serialized create_image_struct (payload of a .dat file)
+        straight to the device.  n_image / n_ang: sizes of the outputs (nx*ny*nv, na*nb)."""
+        buf = np.frombuffer(payload, np.uint8)
+        image, I_ang = np.empty(n_image), np.empty(n_ang)
+        fc, nf = C.c_uint(0), C.c_int(0)
+        failed = np.zeros(abi.N_FAILED_MAX, abi.ray_dtype)
+        rc = self._check(self.L.rtb200_create_image_from_dat(
+            self.h, buf.ctypes.data, buf.size, flags, _addr(image), _addr(I_ang), C.byref(fc),
+            failed.ctypes.data_as(C.POINTER(abi.Ray)), abi.N_FAILED_MAX, C.byref(nf)))
+        self.failure_code, self.n_failed = fc.value, nf.value
+        if rc == abi.RAYS_FAILED and raise_on_failed:
+            raise RaysFailed(fc.value, failed[:min(nf.value, abi.N_FAILED_MAX)])
         return image, I_ang
 
     def trace_rays(self, problem, rays, method, scale, image=None, I_ang=None):

@@ -94,3 +94,54 @@ def test_c_parser_matches_python(name, request, rtlib):
     # malformed input is refused, not crashed on
     bad = C.create_string_buffer(payload[:1000], 1000)
     assert L.rtb200_parse_dat(bad, 1000, C.byref(cp), None, None) == abi.ERR_FORMAT
+
+
+def _plain(p):
+    """The same problem without the off-path extras of the file it came from (the C++ writer
+    emits neutral values for them)."""
+    def grid(g, euv):
+        if g is None:
+            return None
+        return abi.BeamGrid(g.x, g.y, g.a, g.b, g.dx, g.dy, g.da, g.db, dv=g.dv if euv else None, dz=g.dz)
+    gain = [abi.Gain(g.x, g.y, g.n, g.g0, g.E0, g.gv) for g in p.gain]
+    return abi.Problem(grid(p.euv_beam, True), gain, grid(p.seed_beam, False), p.seed, p.N_start, p.N_parallel)
+
+
+@pytest.mark.parametrize("name", ["ase_small", "seed_small"])
+def test_cpp_writer_matches_python_writer(name, request, rtlib):
+    """rtb200_write_dat (create_image_struct::pack restated in C++) produces the bytes of the
+    Python writer, and both parsers read them back."""
+    p, extra = request.getfixturevalue(name)
+    q = _plain(p)
+    want = rt.pack_payload(q, extra["dat_golden_image"], extra["dat_golden_I_ang"])
+    got = rtlib.write_dat_payload(q, extra["dat_golden_image"], extra["dat_golden_I_ang"])
+    assert got == want
+    r, img, ang = rt.parse_payload(got)
+    a, b = problem_io.problem_arrays(p), problem_io.problem_arrays(r)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(img, extra["dat_golden_image"])
+    # without golden arrays
+    assert rtlib.write_dat_payload(q) == rt.pack_payload(q)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                     "oracle", "_ref", "libref_oracle.so")),
+                    reason="oracle/_ref (the reference built from its sources) not present")
+def test_reference_loads_what_the_cpp_writer_wrote(tmp_path, ase_small, rtlib):
+    """The unmodified reference's loader (create_image_struct::unpack) accepts the C++ writer's
+    output and computes the fixture's image from it."""
+    from oracle import pyoracle
+    p, extra = ase_small
+    q = _plain(p)
+    q.N_start, q.N_parallel = 7, 61
+    payload = rtlib.write_dat_payload(q)
+    f = str(tmp_path / "w.dat")
+    with open(f, "wb") as fh:
+        fh.write(struct.pack("<Q", len(payload)) + payload)
+    R = pyoracle.Reference(f)
+    img, ang, _ = R.create_image("cpu")
+    R.close()
+    o = pyoracle.Oracle().create_image(q)
+    assert np.array_equal(img, o["image"]) and np.array_equal(ang, o["I_ang"])
+    assert np.linalg.norm(img) > 0

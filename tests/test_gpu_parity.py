@@ -323,3 +323,27 @@ def test_launch_after_create_image_uses_the_staged_problem(ase_small, ctx):
     img3, _ = fresh.create_image(q)
     fresh.close()
     assert np.array_equal(img2, img3) and not np.array_equal(img2, img)
+
+
+@pytest.mark.parametrize("name", ["ase_small", "seed_small"])
+def test_create_image_from_dat_bytes(name, request, ctx):
+    """rtb200_create_image_from_dat: the serialized problem (unaligned byte stream; the large
+    arrays are read once, from the stream into the pinned blob) gives the bits of the array form."""
+    import raytrace_miniapp_b200 as rt
+    p, extra = request.getfixturevalue(name)
+    stride = 1 if name == "ase_small" else 53
+    p.N_start, p.N_parallel = (0, 1) if stride == 1 else (5, stride)
+    try:
+        payload = b"\x00" + rt.pack_payload(p)  # one more byte of misalignment for good measure
+        e = p.euv_beam
+        img, ang = ctx.create_image_from_dat(memoryview(payload)[1:], e.nx * e.ny * e.nv, e.na * e.nb)
+        ref_img, ref_ang = ctx.create_image(p)
+    finally:
+        p.N_start, p.N_parallel = 0, 1
+    if name == "ase_small":
+        assert np.array_equal(img, ref_img)
+    else:  # scatter binning: atomics in another order
+        assert rel_l2(img, ref_img) < 1e-13
+    assert rel_l2(ang, ref_ang) < 1e-13
+    with pytest.raises(Exception):
+        ctx.create_image_from_dat(payload[1:200], 8, 8)
