@@ -161,11 +161,9 @@ def run_reference(args):
 
 
 def lib_hash():
-    """sha256 of the product library that is loaded (first 16 hex digits): profile figures are
-    only quoted next to a run of the very build they were captured from."""
-    import hashlib
-    from raytrace_miniapp_b200 import lib as rl
-    return hashlib.sha256(open(rl.library_path(), "rb").read()).hexdigest()[:16]
+    """Hash of the product library's sources + build flags (see build.source_hash)."""
+    from raytrace_miniapp_b200 import build as rbuild
+    return rbuild.source_hash()
 
 
 def ncu_figures():
@@ -386,7 +384,7 @@ def run_gpu(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         prof = ncu_figures()
-        prof_ok = bool(prof) and prof.get("lib_sha16") == lib_hash()
+        prof_ok = bool(prof) and prof.get("src_sha16") == lib_hash()
         step_s = ms_per_step * 1e-3
         upd_local = W_upd / world  # per rank (weak: identical shares)
         peak_tflops = fp64_peak * 2 / 1e12
@@ -410,10 +408,10 @@ def run_gpu(args):
                           "device time of the whole step (march + integration); peak = DFMA "
                           "micro-benchmark of this run (%.3e FP64 lane-instr/s; MEASURED_PEAKS.json has "
                           "no FP64 entry)" % fp64_peak,
-            "traffic_note": "dram read+write bytes per step of both kernels (ncu --set full of this very "
-                            "library build, profiles/r02_traffic.json): the march->integrate hand-off "
+            "traffic_note": "dram read+write bytes per step of both kernels (ncu --set full of these very "
+                            "sources, profiles/r02_traffic.json): the march->integrate hand-off "
                             "records, not re-reads of the inputs" if prof_ok else
-                            "null: no ncu capture of this library build is committed (sha mismatch)",
+                            "null: no ncu capture of these sources is committed (source hash mismatch)",
             "fp64_peak_lane_instr_per_s": fp64_peak,
             "per_kernel": {
                 "march_flat_kernel": {"ms": main["march_ms"], "share_of_step": main["march_ms"] / ms_per_step,
@@ -429,7 +427,7 @@ def run_gpu(args):
                     "note": "algorithmic bytes (gain planes in, image / I_ang out) over the step; the "
                             "path is instruction-issue / FP64 bound, not HBM-bound"}}
         if prof_ok:  # pipe-busy figures of the same build (static: measured under ncu, not in this run)
-            roofline["ncu_same_build"] = {k: prof[k] for k in prof if k not in ("lib_sha16", "source")}
+            roofline["ncu_same_build"] = {k: prof[k] for k in prof if k not in ("src_sha16", "source")}
         launches_per_step = main["launches"] // K
         if job.sharded and job.rows is not None:
             launches_per_step += 1  # the un-permute kernel
@@ -448,7 +446,7 @@ def run_gpu(args):
             "image_time_ms_device": ms_per_step,
             "kernel_ms_per_step": {"march": main["march_ms"], "integrate": main["integrate_ms"]},
             "image_l2_norm": image_norm,
-            "lib_sha16": lib_hash(),
+            "src_sha16": lib_hash(),
             "roofline": roofline,
             "wall_s_timed_region": main["wall_s"],
         }

@@ -4,7 +4,7 @@
  * into, called by or shipped with the product library (librtb200.so).  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks this file bit-for-bit
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks this file bit-for-bit
  * against the reference's own RayTraceImageCPULoop compiled from /root/reference (oracle/_ref,
  * see oracle/Makefile) on ASE_small.dat and seed_small.dat, and tests/golden/ holds those
  * reference outputs so the check also runs where /root/reference does not exist.

@@ -24,6 +24,18 @@ def _nvcc():
     raise RuntimeError("nvcc not found: the rtb200 CUDA library cannot be built")
 
 
+def source_hash():
+    """sha256 (first 16 hex digits) over the library's sources and build flags: identifies a build
+    of the kernels across machines (the .so itself is not bit-reproducible).  Profile figures
+    are only quoted next to a run of the very sources they were captured from."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in sorted(SOURCES + HEADERS):
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True

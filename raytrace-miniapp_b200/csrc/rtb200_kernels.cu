@@ -1638,9 +1638,36 @@ __global__ void __launch_bounds__(256) fdiv_check_kernel(unsigned b_first, unsig
         atomicAdd(&out[0], bad);
 }
 
+// Exhaustive check of fsqrt_refined and of the reciprocal that follows it in normalize_s:
+// significands [b_first, b_first + b_count) at binary exponents eb and eb + 1 (both parities).
+__global__ void __launch_bounds__(256) fsqrt_check_kernel(unsigned b_first, unsigned b_count, int eb,
+                                                          unsigned long long *out)
+{
+    const unsigned long long tid = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long bad = 0;
+    for (unsigned long long w = tid; w < 2ull * b_count; w += (unsigned long long) gridDim.x * blockDim.x) {
+        const unsigned bm = b_first + (unsigned) (w >> 1);
+        const float x = __uint_as_float(((unsigned) (eb + (int) (w & 1u) + 127) << 23) | (bm & 0x7fffffu));
+        const float got = fsqrt_refined(x), want = __fsqrt_rn(x);
+        const float rgot = fdiv_refined(1.0f, got, frcp_refined(got));
+        const float rwant = __double2float_rn(__ddiv_rn(1.0, (double) want));
+        if (__float_as_uint(got) != __float_as_uint(want) || __float_as_uint(rgot) != __float_as_uint(rwant)) {
+            bad++;
+            out[1] = __float_as_uint(x);
+            out[2] = __float_as_uint(got);
+        }
+    }
+    if (bad)
+        atomicAdd(&out[0], bad);
+}
+
 void launch_fdiv_check(unsigned b_first, unsigned b_count, int ea, int eb, int variant,
                        unsigned long long *out, cudaStream_t st)
 {
+    if (variant == 2) {
+        fsqrt_check_kernel<<<148 * 16, 256, 0, st>>>(b_first, b_count, eb, out);
+        return;
+    }
     fdiv_check_kernel<<<148 * 16, 256, 0, st>>>(b_first, b_count, ea, eb, variant, out);
 }
 

@@ -23,3 +23,11 @@ def test_refined_division_is_correctly_rounded(ctx):
     # the detector itself: without the correction step the quotient is only faithful
     bad, a, b = ctx.check_fdiv(12345, 8, 0, 0, variant=1)
     assert bad > 1000, bad
+
+
+def test_branch_free_sqrt_and_reciprocal_exhaustive(ctx):
+    """normalize_s: fsqrt_refined and the reciprocal after it, every significand, both exponent
+    parities, at the centre and at both ends of the admitted range 2^-60 .. 2^60."""
+    for eb in (0, -60, 58, -31, 30):
+        bad, x, got = ctx.check_fdiv(0, 1 << 23, 0, eb, variant=2)
+        assert bad == 0, (eb, x, got)
