@@ -37,13 +37,13 @@ def configs():
     yield "ASE_small", "config 1 (reference fixture)", small, 1
     yield "seed_small", "config 1 (reference fixture)", seed, 1
     yield "ASE_medium-synth", "config 2 (stand-in for the missing ASE_medium.dat)", synth.ase_medium_synth(small), 1
-    yield "seed_medium-synth", "config 2 (stand-in for the missing seed_medium.dat)", synth.seed_medium_synth(seed), 16
+    yield "seed_medium-synth", "config 2 (stand-in for the missing seed_medium.dat)", synth.seed_medium_synth(seed), 1
     yield "S4 (gain 2x/axis, image 2x/axis)", "config 4", synth.s4(small, 2, 2), 1
     yield "S4b (gain 4x/axis, image 2x/axis)", "config 4", synth.s4(small, 4, 2), 1
-    yield "S4x (gain 8x/axis: gv 35 MB/plane, image 2x/axis)", "config 4 (lineshape tables beyond L2)", synth.s4(small, 8, 2), 4
+    yield "S4x (gain 8x/axis: gv 35 MB/plane, image 2x/axis)", "config 4 (lineshape tables beyond L2)", synth.s4(small, 8, 2), 1
     for K, af in ((52, 1), (99, 1), (128, 1), (256, 1), (512, 1), (52, 2), (512, 2), (128, 4)):
         yield ("spectral K=%d, angles x%d" % (K, af), "config 5", synth.spectral(small, K, angle_factor=af),
-               1 if K * af * af <= 512 else 4)
+               1)
 
 
 def main():
