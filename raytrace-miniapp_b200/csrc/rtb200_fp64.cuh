@@ -8,8 +8,11 @@
 // The stated tolerance of the path is 1e-10 relative on the image, so exp and the division are
 // evaluated to ~2e-16 / ~2e-14 relative with a fraction of the instructions of the IEEE library
 // routines (which cost 18 + 10 FP64 instructions plus slow-path branches):
-//   exp : x = (64 m + j) ln2/64 + r,  exp(x) = 2^m * 2^(j/64) * (1 + r*q(r)),  |r| <= ln2/128,
-//         2^(j/64) from a 64-entry table, q of degree 4  -> 10 FP64 instructions;
+//   exp : x = (128 m + j) ln2/128 + r,  exp(x) = 2^m * 2^(j/128) * (1 + r*q(r)),  |r| <= ln2/256,
+//         2^(j/128) from a 128-entry table, q of degree 3 (the degree-5 Taylor polynomial with
+//         its last term economised, tools/gen_exptab.py), ONE correctly rounded ln2/128 in the
+//         reduction (abs error of r: 1.8e-19 * |128 m + j|, i.e. 3e-17 * |x|)
+//                                                               -> 8 FP64 instructions;
 //   1/gl: single-precision reciprocal seed + one Newton step in double -> 2 FP64 instructions.
 // Written __host__ __device__ so tests/hostsim can check it against libm without a GPU.
 #pragma once
@@ -23,17 +26,17 @@ namespace rtb {
 // Constants of the update, as an array so that the kernels can keep them in the kernel
 // PARAMETER bank (DevProblem::kfp): c[0x0][..] is directly addressable as an FP64 operand,
 // which avoids materialising 64-bit immediates (2 UMOV per use) or LDC loads in the hot loop.
-#define RTB_K_64_OVER_LN2 0
-#define RTB_K_LN2_64_HI 1
-#define RTB_K_LN2_64_LO 2
-#define RTB_K_C5 3
+#define RTB_K_N_OVER_LN2 0
+#define RTB_K_LN2_OVER_N 1 /* negated */
+#define RTB_K_C1 2
+#define RTB_K_C3 3
 #define RTB_K_C4 4
-#define RTB_K_C3 5
-#define RTB_K_THIRD 6
+#define RTB_K_THIRD 5
 #define RTB_K_COUNT 8
 #define RTB_K_VALUES                                                                             \
-    RTB_EXP_64_OVER_LN2, -RTB_EXP_LN2_64_HI, -RTB_EXP_LN2_64_LO, 1.0 / 120.0, 1.0 / 24.0,        \
-        1.0 / 6.0, 0.3333333333, 0.0
+    RTB_EXP_N_OVER_LN2, -RTB_EXP_LN2_OVER_N, RTB_EXP_C1, RTB_EXP_C3, RTB_EXP_C4, 0.3333333333,   \
+        0.0, 0.0
+#define RTB_EXP_TABLE_SIZE (1 << RTB_EXP_TABLE_BITS)
 
 RTB_HD double fma64(double a, double b, double c)
 {
@@ -73,34 +76,31 @@ RTB_HD double scale_pow2(double e, int m) // e * 2^m for a normal e and a normal
 // the constants pinned in registers and the table read by explicit shared-memory loads.
 struct ArrayConsts {
     const double *kc; // RTB_K_VALUES
-    const double *T;  // 2^(j/64), j = 0..63
-    RTB_HD double l2e() const { return kc[RTB_K_64_OVER_LN2]; }
-    RTB_HD double hi() const { return kc[RTB_K_LN2_64_HI]; }
-    RTB_HD double lo() const { return kc[RTB_K_LN2_64_LO]; }
-    RTB_HD double c5() const { return kc[RTB_K_C5]; }
-    RTB_HD double c4() const { return kc[RTB_K_C4]; }
+    const double *T;  // 2^(j/128), j = 0..127
+    RTB_HD double l2e() const { return kc[RTB_K_N_OVER_LN2]; }
+    RTB_HD double nln2() const { return kc[RTB_K_LN2_OVER_N]; }
+    RTB_HD double c1() const { return kc[RTB_K_C1]; }
     RTB_HD double c3() const { return kc[RTB_K_C3]; }
+    RTB_HD double c4() const { return kc[RTB_K_C4]; }
     RTB_HD double third() const { return kc[RTB_K_THIRD]; }
     RTB_HD double tab(int j) const { return T[j]; }
 };
 
-// exp(x) for |x| < 700 (the caller routes everything else to the library exp).  The range
-// reduction uses ln2/64 split in two parts: accurate to ~2e-16 over the whole range.
+// exp(x) for |x| < 700 (the caller routes everything else to the library exp): relative error
+// <= 4e-16 + 3.4e-17*|x| (tests/test_fp64_update.py), against the path's tolerance of 1e-10.
 template <class KC>
 RTB_HD double exp_core(double x, const KC &C)
 {
     const double t = fma64(x, C.l2e(), RTB_EXP_MAGIC);
     const int n = lo32(t);
     const double tn = t - RTB_EXP_MAGIC;
-    double r = fma64(tn, C.hi(), x);
-    r = fma64(tn, C.lo(), r);
-    double q = fma64(r, C.c5(), C.c4());
-    q = fma64(r, q, C.c3());
+    const double r = fma64(tn, C.nln2(), x);
+    double q = fma64(r, C.c4(), C.c3());
     q = fma64(r, q, 0.5);
-    q = fma64(r, q, 1.0);
-    const double Tj = C.tab(n & 63);
+    q = fma64(r, q, C.c1());
+    const double Tj = C.tab(n & (RTB_EXP_TABLE_SIZE - 1));
     const double e = fma64(Tj, r * q, Tj);
-    return scale_pow2(e, n >> 6);
+    return scale_pow2(e, n >> RTB_EXP_TABLE_BITS);
 }
 
 template <class KC>
@@ -122,7 +122,7 @@ RTB_HD double ase_update_small(double Iv, double gl, double el, const KC &C)
     return fma64(el, c, Iv * e);
 }
 
-// The exp branch for |gl| < 700 (15 FP64 instructions); rcp_seed is a single-precision
+// The exp branch for |gl| < 700 (13 FP64 instructions); rcp_seed is a single-precision
 // approximation of 1/gl.  el/gl*(e - 1) + Iv*e is evaluated as u*e + (Iv*e - u), u = el/gl.
 template <class KC>
 RTB_HD double ase_update_large(double Iv, double gl, double el, float rcp_seed, const KC &C)

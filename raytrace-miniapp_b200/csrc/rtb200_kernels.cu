@@ -424,11 +424,11 @@ __device__ __noinline__ double ase_update_library(double Iv, double gl, double e
     return el / gl * (e - 1.0) + Iv * e;
 }
 
-__constant__ double c_exp_table[64] = { RTB_EXP_TABLE_VALUES };
+__constant__ double c_exp_table[RTB_EXP_TABLE_SIZE] = { RTB_EXP_TABLE_VALUES };
 
 __device__ __forceinline__ void load_exp_table(double *T)
 {
-    for (int i = threadIdx.x; i < 64; i += blockDim.x)
+    for (int i = threadIdx.x; i < RTB_EXP_TABLE_SIZE; i += blockDim.x)
         T[i] = c_exp_table[i];
     __syncthreads();
 }
@@ -438,6 +438,16 @@ __device__ __forceinline__ float rcp_approx(float x)
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+}
+
+// A value every lane of the warp holds, re-issued through a warp reduction: the result lives in
+// a uniform register, so the compiler KNOWS that branches and loop bounds derived from it are
+// warp-uniform (no divergence check in front of the votes, no reconvergence points).
+__device__ __forceinline__ unsigned uniform_u32(unsigned v) { return __reduce_or_sync(0xffffffffu, v); }
+// Lane j's value for the whole warp, as a uniform value (see uniform_u32).
+__device__ __forceinline__ unsigned uniform_from_lane(unsigned v, int lane, int j)
+{
+    return __reduce_or_sync(0xffffffffu, lane == j ? v : 0u);
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -548,8 +558,8 @@ __device__ __forceinline__ int integrate_ray(const DevProblem &P, const SegRec *
 // (measured: ~30 of 150 instructions per record were such reloads, profiles/r01).  The exp
 // table is addressed by an explicit shared-memory load.
 struct PinnedConsts {
-    double l2e_, hi_, lo_, c5_, c4_, c3_, third_;
-    unsigned tab_; // shared-space address of the 2^(j/64) table
+    double l2e_, nln2_, c1_, c3_, c4_, third_;
+    unsigned tab_; // shared-space address of the 2^(j/128) table
     __device__ __forceinline__ static double pin(const double *p)
     {
         double x;
@@ -558,23 +568,21 @@ struct PinnedConsts {
     }
     __device__ __forceinline__ PinnedConsts(const double *kc, const double *T)
     {
-        l2e_ = pin(kc + RTB_K_64_OVER_LN2);
-        hi_ = pin(kc + RTB_K_LN2_64_HI);
-        lo_ = pin(kc + RTB_K_LN2_64_LO);
-        c5_ = pin(kc + RTB_K_C5);
-        c4_ = pin(kc + RTB_K_C4);
+        l2e_ = pin(kc + RTB_K_N_OVER_LN2);
+        nln2_ = pin(kc + RTB_K_LN2_OVER_N);
+        c1_ = pin(kc + RTB_K_C1);
         c3_ = pin(kc + RTB_K_C3);
+        c4_ = pin(kc + RTB_K_C4);
         third_ = pin(kc + RTB_K_THIRD);
         // the shuffle makes the shared-memory address opaque: otherwise the compiler rebuilds it
         // from the CTA's shared window (4 uniform-datapath instructions) at every use
         tab_ = __shfl_sync(0xffffffffu, (unsigned) __cvta_generic_to_shared(T), 0);
     }
     __device__ __forceinline__ double l2e() const { return l2e_; }
-    __device__ __forceinline__ double hi() const { return hi_; }
-    __device__ __forceinline__ double lo() const { return lo_; }
-    __device__ __forceinline__ double c5() const { return c5_; }
-    __device__ __forceinline__ double c4() const { return c4_; }
+    __device__ __forceinline__ double nln2() const { return nln2_; }
+    __device__ __forceinline__ double c1() const { return c1_; }
     __device__ __forceinline__ double c3() const { return c3_; }
+    __device__ __forceinline__ double c4() const { return c4_; }
     __device__ __forceinline__ double third() const { return third_; }
     __device__ __forceinline__ double tab(int j) const
     {
@@ -608,17 +616,27 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
         // the plane look-up and the 64-bit address arithmetic.
         __syncwarp();
         unsigned gvl_abs = 0u;
+        bool nonzero = false;
         if (lane < cnt) {
             const int4 rv = __ldg(reinterpret_cast<const int4 *>(&seg[c0 + lane]));
             const float *row = s_gv[(c0 + lane) / RTB_N_SUB + 1] + (size_t) rv.z * K;
             const unsigned long long ra = reinterpret_cast<unsigned long long>(row);
             gvl_abs = (unsigned) rv.x & 0x7fffffffu;
+            // gvl == 0 && evl == 0 (either sign of zero): gl = el = 0, the update is the identity
+            nonzero = (((unsigned) rv.x | (unsigned) rv.y) & 0x7fffffffu) != 0u;
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slab + 16u * (unsigned) lane),
                          "r"((unsigned) rv.x), "r"((unsigned) rv.y), "r"((unsigned) ra),
                          "r"((unsigned) (ra >> 32))
                          : "memory");
         }
         __syncwarp();
+        // The records that change anything, as a warp-uniform bit mask: the walk below visits
+        // exactly these (30 % of the records of ASE_medium-synth lie outside the plasma), and
+        // everything that steers it - mask, loop counters, vote results - is uniform by
+        // construction, so no branch of the walk needs a divergence check or a reconvergence point.
+        unsigned todo = __ballot_sync(0xffffffffu, nonzero);
+        if (todo == 0u)
+            continue;
         // exp-range test of the records (|gl| >= 700, inf, NaN -> library exp): needed for none
         // of these records if max|gvl| * max|gv| stays below 700 (bit patterns order like the
         // magnitudes, NaN above everything; the comparison is false for NaN)
@@ -627,8 +645,6 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
             !(__fmul_rn(__fmul_rn(gvl_max, __uint_as_float(P.gv_absmax_bits)), 1.000001f) < 700.0f);
         // The update of one record; `g` are the lineshape values of this lane's bins.
         auto update = [&](float gvl, float evl, const float (&g)[KS]) {
-            if (gvl == 0.0f && evl == 0.0f)
-                return; // gl = el = 0: the update is the identity
             // Branch decisions by warp votes: their results are uniform predicates, so the
             // dispatch below costs a branch each and nothing else.
             float glf[KS], elf[KS];
@@ -676,21 +692,33 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
             for (int q = 0; q < KS; q++)
                 g[q] = __ldg(row + koff[q]);
         };
+        // next record of the mask (the mask is not empty)
+        auto pop = [&todo]() {
+            const int j = __ffs((int) todo) - 1;
+            todo &= todo - 1u;
+            return j;
+        };
         // Two records per trip with ping-pong registers: the row of the next record is
-        // requested before the current one is integrated, without rotating registers.
+        // requested before the current one is integrated, without rotating registers.  Past the
+        // last record the prefetch re-reads it (unused), which costs less than a guarded fetch.
         uint4 eA, eB;
         float gA[KS], gB[KS];
-        fetch(0, eA, gA);
-        for (int j = 0;; j += 2) {
-            // the prefetch index is clamped instead of guarded: past the end it re-reads the last
-            // record (unused), which costs less than a branch and a reconvergence point
-            fetch(min(j + 1, cnt - 1), eB, gB);
+        int j = pop();
+        fetch(j, eA, gA);
+        for (;;) {
+            const bool lastA = todo == 0u;
+            if (!lastA)
+                j = pop();
+            fetch(j, eB, gB);
             update(__uint_as_float(eA.x), __uint_as_float(eA.y), gA);
-            if (j + 1 >= cnt)
+            if (lastA)
                 break;
-            fetch(min(j + 2, cnt - 1), eA, gA);
+            const bool lastB = todo == 0u;
+            if (!lastB)
+                j = pop();
+            fetch(j, eA, gA);
             update(__uint_as_float(eB.x), __uint_as_float(eB.y), gB);
-            if (j + 2 >= cnt)
+            if (lastB)
                 break;
         }
     }
@@ -820,13 +848,13 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, RTB_OWNER_MINBLOCKS)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double part[RTB_OWNER_WARPS][KS * 32];
-    __shared__ double exp_tab[64];
+    __shared__ double exp_tab[RTB_EXP_TABLE_SIZE];
     __shared__ uint4 rec_slab[RTB_OWNER_WARPS][32]; // per-warp record + row-address slab
     const float **s_gv = reinterpret_cast<const float **>(smem_raw); // [N] gv base pointers
     for (int i = threadIdx.x; i < P.N; i += blockDim.x)
         s_gv[i] = P.planes[i].gv;
     load_exp_table(exp_tab); // includes __syncthreads()
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = (int) uniform_u32(threadIdx.x >> 5);
     const long long p = phys_pixel(P, c, c.pix0 + blockIdx.x);
     const PixelRays pr = pixel_rays(P, p);
     const int S = (P.N - 1) * RTB_N_SUB;
@@ -846,8 +874,7 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, RTB_OWNER_MINBLOCKS)
         koff[q] = k < K ? k : (live > 0 ? 32 * q + (k - K) % live : K - 1);
     }
     const PinnedConsts KC(P.kfp_g, exp_tab);
-    const unsigned slab_addr =
-        __shfl_sync(0xffffffffu, (unsigned) __cvta_generic_to_shared(&rec_slab[warp][0]), 0);
+    const unsigned slab_addr = uniform_u32((unsigned) __cvta_generic_to_shared(&rec_slab[warp][0]));
     // The warp's rays are t = warp, warp + 8, ...; what is per ray and not per bin (hand-off meta
     // word, angular bin) is looked up by one lane per ray, 32 rays at a time.
     for (int t0 = warp; t0 < pr.cnt; t0 += 32 * RTB_OWNER_WARPS) {
@@ -867,8 +894,8 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, RTB_OWNER_MINBLOCKS)
         for (int j = 0; j < n_here; j++) {
             const int t = t0 + j * RTB_OWNER_WARPS;
             const long long slot = slot0 + t;
-            const unsigned meta = __shfl_sync(0xffffffffu, meta_l, j);
-            const int bin = __shfl_sync(0xffffffffu, bin_l, j);
+            const unsigned meta = uniform_from_lane(meta_l, lane, j);
+            const int bin = (int) uniform_from_lane((unsigned) bin_l, lane, j);
             if (meta & RTB_META_INVALID)
                 continue; // error -1, reported by the march
             double Iv[KS];
@@ -926,21 +953,20 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, 3)
     constexpr int KS = 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double part[RTB_OWNER_WARPS][KS * 32];
-    __shared__ double exp_tab[64];
+    __shared__ double exp_tab[RTB_EXP_TABLE_SIZE];
     __shared__ uint4 rec_slab[RTB_OWNER_WARPS][32];
     const float **s_gv = reinterpret_cast<const float **>(smem_raw); // [N] gv base pointers
     for (int i = threadIdx.x; i < P.N; i += blockDim.x)
         s_gv[i] = P.planes[i].gv;
     load_exp_table(exp_tab); // includes __syncthreads()
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = (int) uniform_u32(threadIdx.x >> 5);
     const long long p = phys_pixel(P, c, c.pix0 + blockIdx.x);
     const PixelRays pr = pixel_rays(P, p);
     const int S = (P.N - 1) * RTB_N_SUB;
     const int K = P.K;
     const long long slot0 = (long long) blockIdx.x * P.ab_max;
     const PinnedConsts KC(P.kfp_g, exp_tab);
-    const unsigned slab_addr =
-        __shfl_sync(0xffffffffu, (unsigned) __cvta_generic_to_shared(&rec_slab[warp][0]), 0);
+    const unsigned slab_addr = uniform_u32((unsigned) __cvta_generic_to_shared(&rec_slab[warp][0]));
     const int pi = __ldg(&P.pixI[pr.i]), pj = __ldg(&P.pixJ[pr.j]);
     const bool store = o.compact || (pi >= 0 && pj >= 0);
     const size_t opix = o.compact ? (size_t) (c.pix0 + blockIdx.x) : (size_t) pi + (size_t) pj * P.nx;
@@ -972,8 +998,8 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, 3)
             for (int j = 0; j < n_here; j++) {
                 const int t = t0 + j * RTB_OWNER_WARPS;
                 const long long slot = slot0 + t;
-                const unsigned meta = __shfl_sync(0xffffffffu, meta_l, j);
-                const int bin = __shfl_sync(0xffffffffu, bin_l, j);
+                const unsigned meta = uniform_from_lane(meta_l, lane, j);
+                const int bin = (int) uniform_from_lane((unsigned) bin_l, lane, j);
                 if (meta & RTB_META_INVALID)
                     continue; // error -1, reported by the march
                 double Iv[KS];
@@ -1173,7 +1199,7 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
     integrate_scatter_kernel(const DevProblem P, const Chunk c, const Handoff h, const Outputs o)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double exp_tab[64];
+    __shared__ double exp_tab[RTB_EXP_TABLE_SIZE];
     // dynamic shared memory: per-warp record + row-address slabs (8 x RTB_SLAB_RECORDS x 16 B),
     // then the gv base pointers of the planes
     uint4 *rec_slab = reinterpret_cast<uint4 *>(smem_raw);
@@ -1455,7 +1481,7 @@ __global__ void __launch_bounds__(256)
     path_intensity_kernel(const DevProblem P, const Chunk c, const Handoff h, float *path_I, int *error)
 {
     constexpr int KS = 4;
-    __shared__ double exp_tab[64];
+    __shared__ double exp_tab[RTB_EXP_TABLE_SIZE];
     load_exp_table(exp_tab);
     const ArrayConsts KC{ P.kfp, exp_tab };
     const int lane = threadIdx.x & 31;

@@ -139,7 +139,7 @@ int hostsim_find_cell_fast(const double *X, int n, double Yd)
 }
 
 // FP64 update doors (rtb200_fp64.cuh): the fast exp and the two update branches.
-static const double k_exp_table[64] = { RTB_EXP_TABLE_VALUES };
+static const double k_exp_table[RTB_EXP_TABLE_SIZE] = { RTB_EXP_TABLE_VALUES };
 static const double k_fp[RTB_K_COUNT] = { RTB_K_VALUES };
 static const ArrayConsts k_consts = { k_fp, k_exp_table };
 void hostsim_exp(const double *x, double *y, int n)
