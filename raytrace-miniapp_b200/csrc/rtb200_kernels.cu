@@ -346,17 +346,20 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
         // warp has run dry).  Keeping the refill code out of this loop keeps its live ranges
         // out of the hot path.
         GlobalSinkT<PATH> sink{ h.seg, h.path, L, S, L * (unsigned) S };
-        for (unsigned trips = 0;; ++trips) { // (warp-uniform counter)
+        // lanes without a ray and with none left to claim (set by the refill above only)
+        const unsigned dead = __ballot_sync(0xffffffffu, (m.st & RTB_ST_DEAD) != 0u);
+        unsigned marching;
+        unsigned trips = 0; // (warp-uniform counter)
+        do {
             // every lane takes the trip (finished lanes fall through): see flat_trip
             flat_trip(m, K, sink);
-            // hang guard: no ray takes 2^22 trips; whatever is still marching is given up
-            if (trips > (1u << 22) && flat_phase(m) != PH_DONE)
-                m.st = (m.st | RTB_ST_HUNG | RTB_ST_PHASE); // PH_DONE == all phase bits
-            // lanes that can take a new ray / lanes that are marching
-            const unsigned refill = __ballot_sync(0xffffffffu, (m.st & (RTB_ST_PHASE | RTB_ST_DEAD)) == (unsigned) PH_DONE);
-            if (__popc(refill) >= RTB_REFILL_MIN || __all_sync(0xffffffffu, flat_phase(m) == PH_DONE))
-                break;
-        }
+            // ONE vote per trip: the lanes that are marching; the others can take a new ray
+            // unless they are dead.  The loop ends when enough lanes wait for a refill, when the
+            // warp has run dry, or at the hang guard (no ray takes 2^22 trips).
+            marching = __ballot_sync(0xffffffffu, flat_phase(m) != PH_DONE);
+        } while (marching != 0u && __popc(~(marching | dead)) < RTB_REFILL_MIN && ++trips <= (1u << 22));
+        if (trips > (1u << 22) && flat_phase(m) != PH_DONE) // whatever is still marching is given up
+            m.st = (m.st | RTB_ST_HUNG | RTB_ST_PHASE);     // PH_DONE == all phase bits
     }
     if (COUNT) {
         unsigned tot = total_steps;
