@@ -291,7 +291,8 @@ int rtb200_measure_fp64_peak(rtb200_ctx *ctx, double *fp64_lane_instr_per_s);
  * division the march uses; variant 1 omits its correction step (a self-test of the detector:
  * it must report mismatches); variant 2 checks the branch-free square root and the reciprocal
  * that follows it in normalize_s (fsqrt_refined) for the significands [b_first, b_first +
- * b_count) at exponents exp_b and exp_b + 1 against the IEEE results (exp_a is ignored). */
+ * b_count) at exponents exp_b and exp_b + 1 against the IEEE results (exp_a is ignored);
+ * variant 3 is variant 0 through the packed two-quotient form the step uses (FFMA2, both lanes). */
 int rtb200_check_fdiv(rtb200_ctx *ctx, unsigned b_first, unsigned b_count, int exp_a, int exp_b,
                       int variant, unsigned long long *mismatches, float *witness_a, float *witness_b);
 

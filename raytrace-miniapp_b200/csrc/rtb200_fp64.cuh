@@ -61,7 +61,13 @@ RTB_HD int lo32(double x)
 RTB_HD double scale_pow2(double e, int m) // e * 2^m for a normal e and a normal result
 {
 #if defined(__CUDA_ARCH__)
+#ifndef RTB_NO_MAD_POW2 // one multiply-add on the high word (left alone the compiler emits shift + mask + add; -1.6 %)
+    int hi;
+    asm("mad.lo.s32 %0, %1, 0x100000, %2;" : "=r"(hi) : "r"(m), "r"(__double2hiint(e)));
+    return __hiloint2double(hi, __double2loint(e));
+#else
     return __hiloint2double(__double2hiint(e) + (m << 20), __double2loint(e));
+#endif
 #else
     long long b;
     memcpy(&b, &e, 8);

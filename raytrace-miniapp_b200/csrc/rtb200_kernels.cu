@@ -1647,6 +1647,30 @@ __global__ void __launch_bounds__(256) fdiv_check_kernel(unsigned b_first, unsig
         const unsigned a0 = (unsigned) (w & 0xffffu) << 7;
         const float b = __uint_as_float(((unsigned) (eb + 127) << 23) | (bm & 0x7fffffu));
         const float r = frcp_refined(b);
+#if defined(__CUDA_ARCH__) && !defined(RTB_NO_F32X2)
+        if (variant == 3) { // the packed form (FFMA2): both lanes, reciprocal refined in the pair as well
+            for (unsigned i = 0; i < 128u; i += 2) {
+                const float a = __uint_as_float(((unsigned) (ea + 127) << 23) | (a0 + i));
+                const float a2 = __uint_as_float(((unsigned) (ea + 127) << 23) | (a0 + i + 1u));
+                float q, q2, p, p2;
+                fdiv_refined2(a, b, a2, b, q, q2);
+                fdiv_refined2_by(a2, a, b, r, p2, p);
+                const float want = __double2float_rn(__ddiv_rn((double) a, (double) b));
+                const float want2 = __double2float_rn(__ddiv_rn((double) a2, (double) b));
+                if (__float_as_uint(q) != __float_as_uint(want) || __float_as_uint(p) != __float_as_uint(want)) {
+                    bad++;
+                    out[1] = __float_as_uint(a);
+                    out[2] = __float_as_uint(b);
+                }
+                if (__float_as_uint(q2) != __float_as_uint(want2) || __float_as_uint(p2) != __float_as_uint(want2)) {
+                    bad++;
+                    out[1] = __float_as_uint(a2);
+                    out[2] = __float_as_uint(b);
+                }
+            }
+            continue;
+        }
+#endif
 #pragma unroll 4
         for (unsigned i = 0; i < 128u; i++) {
             const float a = __uint_as_float(((unsigned) (ea + 127) << 23) | (a0 + i));

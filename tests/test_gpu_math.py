@@ -20,6 +20,11 @@ def test_refined_division_is_correctly_rounded(ctx):
         assert bad == 0, (bad, a, b, ea, eb)
         total += nb << 23
     assert total > 3e9
+    # the packed two-quotient form (FFMA2) the step runs: same slices, both lanes
+    for i, (b0, nb) in enumerate(slices):
+        ea, eb = scales[(i + 2) % len(scales)]
+        bad, a, b = ctx.check_fdiv(b0, nb, ea, eb, variant=3)
+        assert bad == 0, ("packed", bad, a, b, ea, eb)
     # the detector itself: without the correction step the quotient is only faithful
     bad, a, b = ctx.check_fdiv(12345, 8, 0, 0, variant=1)
     assert bad > 1000, bad
