@@ -18,6 +18,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "rtb200_fp64.cuh"
 #include "rtb200_kernels.cuh"
@@ -348,11 +349,11 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
         GlobalSinkT<PATH> sink{ h.seg, h.path, L, S, L * (unsigned) S };
         // lanes without a ray and with none left to claim (set by the refill above only)
         const unsigned dead = __ballot_sync(0xffffffffu, (m.st & RTB_ST_DEAD) != 0u);
-        unsigned marching;
+        unsigned marching = __ballot_sync(0xffffffffu, flat_phase(m) != PH_DONE);
         unsigned trips = 0; // (warp-uniform counter)
         do {
             // every lane takes the trip (finished lanes fall through): see flat_trip
-            flat_trip(m, K, sink);
+            flat_trip(m, K, sink, marching, !exhausted);
             // ONE vote per trip: the lanes that are marching; the others can take a new ray
             // unless they are dead.  The loop ends when enough lanes wait for a refill, when the
             // warp has run dry, or at the hang guard (no ray takes 2^22 trips).
@@ -644,10 +645,14 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
         // of these records if max|gvl| * max|gv| stays below 700 (bit patterns order like the
         // magnitudes, NaN above everything; the comparison is false for NaN)
         const float gvl_max = __uint_as_float(__reduce_max_sync(0xffffffffu, gvl_abs));
-        const bool range_test =
+        const bool need_range_test =
             !(__fmul_rn(__fmul_rn(gvl_max, __uint_as_float(P.gv_absmax_bits)), 1.000001f) < 700.0f);
         // The update of one record; `g` are the lineshape values of this lane's bins.
-        auto update = [&](float gvl, float evl, const float (&g)[KS]) {
+        // (generic over a compile-time flag: the walk below is instantiated with and without the
+        // range test, so the common walk - no record of the chunk can reach |gl| = 700 - carries
+        // neither the test nor its branch)
+        auto update = [&](auto range_tag, float gvl, float evl, const float (&g)[KS]) {
+            constexpr bool range_test = decltype(range_tag)::value;
             // Branch decisions by warp votes: their results are uniform predicates, so the
             // dispatch below costs a branch each and nothing else.
             float glf[KS], elf[KS];
@@ -704,26 +709,32 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
         // Two records per trip with ping-pong registers: the row of the next record is
         // requested before the current one is integrated, without rotating registers.  Past the
         // last record the prefetch re-reads it (unused), which costs less than a guarded fetch.
-        uint4 eA, eB;
-        float gA[KS], gB[KS];
-        int j = pop();
-        fetch(j, eA, gA);
-        for (;;) {
-            const bool lastA = todo == 0u;
-            if (!lastA)
-                j = pop();
-            fetch(j, eB, gB);
-            update(__uint_as_float(eA.x), __uint_as_float(eA.y), gA);
-            if (lastA)
-                break;
-            const bool lastB = todo == 0u;
-            if (!lastB)
-                j = pop();
+        auto walk = [&](auto range_tag) {
+            uint4 eA, eB;
+            float gA[KS], gB[KS];
+            int j = pop();
             fetch(j, eA, gA);
-            update(__uint_as_float(eB.x), __uint_as_float(eB.y), gB);
-            if (lastB)
-                break;
-        }
+            for (;;) {
+                const bool lastA = todo == 0u;
+                if (!lastA)
+                    j = pop();
+                fetch(j, eB, gB);
+                update(range_tag, __uint_as_float(eA.x), __uint_as_float(eA.y), gA);
+                if (lastA)
+                    break;
+                const bool lastB = todo == 0u;
+                if (!lastB)
+                    j = pop();
+                fetch(j, eA, gA);
+                update(range_tag, __uint_as_float(eB.x), __uint_as_float(eB.y), gB);
+                if (lastB)
+                    break;
+            }
+        };
+        if (__builtin_expect(need_range_test, 0))
+            walk(std::true_type{});
+        else
+            walk(std::false_type{});
     }
     bool neg = false, nan = false;
 #pragma unroll
