@@ -218,7 +218,7 @@ __device__ __forceinline__ bool slot_source(const DevProblem &P, const Chunk &c,
 // the plasma early.  The plane descriptors every cell look-up starts from and the sub-segment
 // limits are staged in shared memory once per CTA.
 #ifndef RTB_MARCH_MINBLOCKS
-#define RTB_MARCH_MINBLOCKS 5
+#define RTB_MARCH_MINBLOCKS 6
 #endif
 #ifndef RTB_MARCH_CHUNK
 #define RTB_MARCH_CHUNK 32
