@@ -1487,6 +1487,255 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Seeded image, grid mode (method 2: gain-only integration of the seed spectrum along every ray
+// of the seed beam, binned by the EXIT ray; src/RayTraceImageCPU.cpp:40-60,
+// RayTraceImageHelper.h:569-581): the lean form of integrate_scatter_kernel for what a seeded
+// create_image needs - no per-ray dumps, no explicit ray list, one pass over K <= 32 KS bins.
+// One warp per 64 consecutive ray slots, lane = frequency bin.  What is per ray and not per bin
+// (seed amplitude, destination pixel and angular bin: four index searches) is evaluated by one
+// lane per ray, 32 rays at a time, and handed out as warp-uniform values; the hand-off records of
+// a batch of rays are fetched with coalesced loads into the warp's shared-memory slab; a ray then
+// costs one 16-byte broadcast read, KS lineshape loads and KS DFMAs per record, and KS exp at the
+// end.  Consecutive rays mostly leave the plasma through the same pixel: their spectra are summed
+// in registers and flushed with one set of FP64 atomics when the destination changes.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void seeded_slot_ray(const DevProblem &P, const Chunk &c, long long slot, float &rx,
+                                                float &ry, float &ra, float &rb, int &pi, int &pj, int &ka, int &m)
+{
+    const unsigned lq = (unsigned) slot / (unsigned) P.ab_max; // slots fit 32 bits
+    const long long p = phys_pixel(P, c, c.pix0 + lq);
+    const int t = (int) ((unsigned) slot - lq * (unsigned) P.ab_max);
+    const PixelRays pr = pixel_rays(P, p);
+    const int ab = pr.ab0 + t * (int) P.n_parallel;
+    ka = (int) ((unsigned) ab / (unsigned) P.snb);
+    m = ab - ka * P.snb;
+    pi = pr.i;
+    pj = pr.j;
+    rx = __ldg(&P.sxf[pi]);
+    ry = __ldg(&P.syf[pj]);
+    ra = __ldg(&P.saf[ka]);
+    rb = __ldg(&P.sbf[m]);
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
+    integrate_seeded_kernel(const DevProblem P, const Chunk c, const Handoff h, const Outputs o)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double exp_tab[RTB_EXP_TABLE_SIZE];
+    uint4 *rec_slab = reinterpret_cast<uint4 *>(smem_raw);
+    const float **s_gv = reinterpret_cast<const float **>(smem_raw + 8 * RTB_SLAB_RECORDS * sizeof(uint4)); // [N]
+    for (int i = threadIdx.x; i < P.N; i += blockDim.x)
+        s_gv[i] = P.planes[i].gv;
+    load_exp_table(exp_tab); // includes __syncthreads()
+    const ArrayConsts KC{ P.kfp, exp_tab };
+    const int lane = threadIdx.x & 31;
+    const int warp_in_cta = (int) uniform_u32(threadIdx.x >> 5);
+    const unsigned slab = uniform_u32((unsigned) __cvta_generic_to_shared(rec_slab + warp_in_cta * RTB_SLAB_RECORDS));
+    const int warp_id = (int) (blockIdx.x * (blockDim.x >> 5)) + warp_in_cta;
+    const int n_warps = (int) ((gridDim.x * blockDim.x) >> 5);
+    const int n_slots = (int) ((c.pix1 - c.pix0) * P.ab_max); // fits 31 bits (the host sizes chunks that way)
+    const int S = (P.N - 1) * RTB_N_SUB;
+    const int K = P.K;
+    constexpr int RUN = 64;
+    // this lane's bins: k = lane + 32 q; lanes past the last bin shadow bin K-1 with a zero seed
+    int koff[KS];
+    bool live[KS];
+    double seedv[KS], dv2[KS], acc[KS];
+#pragma unroll
+    for (int q = 0; q < KS; q++) {
+        const int k = lane + 32 * q;
+        live[q] = k < K;
+        koff[q] = min(k, K - 1);
+        seedv[q] = live[q] ? __ldg(&P.seed_fv[k]) : 0.0;
+        dv2[q] = live[q] ? __ldg(&P.dv2[k]) : 0.0;
+        acc[q] = 0.0;
+    }
+    double acc_w = 0.0;
+    int cur_pix = -1, cur_bin = -1; // (warp-uniform)
+    auto flush_pix = [&]() {
+#pragma unroll
+        for (int q = 0; q < KS; q++) {
+            if (cur_pix >= 0 && live[q])
+                atomicAdd(&o.image[(size_t) K * (size_t) cur_pix + (size_t) (lane + 32 * q)], acc[q]);
+            acc[q] = 0.0; // also after a run of rays that left the image (cur_pix < 0): dropped
+        }
+        cur_pix = -1;
+    };
+    auto flush_bin = [&]() { // acc_w: this lane's share of the run's angular-bin sum
+        if (cur_bin >= 0) {
+            const double w = warp_sum(acc_w);
+            if (lane == 0)
+                atomicAdd(&o.I_ang[cur_bin], w);
+        }
+        acc_w = 0.0;
+        cur_bin = -1;
+    };
+    // rays whose records are fetched together: as many as fit the slab
+    int batch = 32;
+    while (batch > 1 && batch * S > RTB_SLAB_RECORDS)
+        batch >>= 1;
+    const int n_runs = (n_slots + RUN - 1) / RUN;
+    for (int run = warp_id; run < n_runs; run += n_warps) {
+        const int slot_end = min((run + 1) * RUN, n_slots);
+        for (int base = run * RUN; base < slot_end; base += 32) {
+            // ---- per ray, one lane each: meta word, seed amplitude, destination ----
+            unsigned meta_l = RTB_META_INACTIVE;
+            double f_l = 0.0;
+            int pix_l = -1, bin_l = -1;
+            if (base + lane < slot_end) {
+                const long long slot = base + lane;
+                meta_l = __ldg(&h.meta[slot]);
+                if (!(meta_l & RTB_META_INACTIVE)) {
+                    float rx, ry, ra, rb;
+                    int pi, pj, ka, m;
+                    seeded_slot_ray(P, c, slot, rx, ry, ra, rb, pi, pj, ka, m);
+                    if (P.seed_fx && !(meta_l & RTB_META_ESCAPED)) {
+                        // calc_seed_inline (:230-247) from the per-index tables
+                        const double fx = __ldg(&P.seed_fx[pi]), fy = __ldg(&P.seed_fy[pj]);
+                        const double fa = __ldg(&P.seed_fa[ka]), fb = __ldg(&P.seed_fb[m]);
+                        if (fx == fx && fy == fy && fa == fa && fb == fb) {
+                            f_l = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(P.seed_f0, fx), fy), fa), fb);
+                            f_l = f_l < 0.0 ? 0.0 : f_l;
+                        }
+                    }
+                    if (!(meta_l & RTB_META_INVALID)) {
+                        float bx = rx, by = ry, ba = ra, bb = rb;
+                        if (P.method != 1) { // forward: bin by the exit ray (RayTraceImageCPU.cpp:40-49)
+                            const float4 e = h.exit_ray[slot];
+                            bx = e.x;
+                            by = e.y;
+                            ba = -e.z;
+                            bb = -e.w;
+                            if (by < 0.0f && P.y_mirror)
+                                by = -by;
+                        }
+                        const int i1 = dev_get_index(P.nx, P.ex, P.edx, (double) bx);
+                        const int i2 = dev_get_index(P.ny, P.ey, P.edy, (double) by);
+                        const int i3 = dev_get_index(P.na, P.ea, P.eda, (double) ba);
+                        const int i4 = dev_get_index(P.nb, P.eb, P.edb, (double) bb);
+                        if (i1 >= 0 && i2 >= 0)
+                            pix_l = i1 + i2 * P.nx;
+                        if (i3 >= 0 && i4 >= 0)
+                            bin_l = i3 + i4 * P.na;
+                    }
+                }
+            }
+            __syncwarp();
+            const int n_here = min(slot_end - base, 32);
+            for (int j0 = 0; j0 < n_here; j0 += batch) {
+                // ---- one coalesced sweep over the records of the next `batch` rays (contiguous in
+                //      the arena); entries outside a ray's visited range are never read ----
+                const int nb = min(batch, n_here - j0);
+                {
+                    const int nrec = nb * S;
+                    const SegRec *src = h.seg + (size_t) (base + j0) * S;
+                    for (int r = lane; r < nrec; r += 32) {
+                        const int4 rv = __ldg(reinterpret_cast<const int4 *>(&src[r]));
+                        const int sg = r % S;
+                        const float *row = s_gv[sg / RTB_N_SUB + 1] + (size_t) rv.z * K;
+                        const unsigned long long ra = reinterpret_cast<unsigned long long>(row);
+                        const unsigned long long gd =
+                            (unsigned long long) __double_as_longlong((double) __int_as_float(rv.x));
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slab + 16u * (unsigned) r),
+                                     "r"((unsigned) gd), "r"((unsigned) (gd >> 32)), "r"((unsigned) ra),
+                                     "r"((unsigned) (ra >> 32))
+                                     : "memory");
+                    }
+                }
+                __syncwarp();
+                for (int jj = 0; jj < nb; jj++) {
+                    const int j = j0 + jj;
+                    const unsigned meta = uniform_from_lane(meta_l, lane, j);
+                    if (meta & RTB_META_INACTIVE)
+                        continue;
+                    const int pix = (int) uniform_from_lane((unsigned) pix_l, lane, j);
+                    const int bin = (int) uniform_from_lane((unsigned) bin_l, lane, j);
+                    const double f = __shfl_sync(0xffffffffu, f_l, j);
+                    if (meta & RTB_META_INVALID)
+                        continue; // error -1, reported by the march
+                    // ---- gain-only integration: gl[k] = sum over records of gvl * gv[cell][k]
+                    //      (the product of two floats is exact in double, so one DFMA per bin and
+                    //      record is the reference's multiply-then-add bit for bit) ----
+                    const int lo = meta & 0xfff, hi = (meta >> 12) & 0xfff;
+                    const unsigned ray_slab = slab + 16u * (unsigned) (jj * S);
+                    double gl[KS];
+#pragma unroll
+                    for (int q = 0; q < KS; q++)
+                        gl[q] = 0.0;
+                    auto fetch = [&](int s, double &gvl, float (&g)[KS]) {
+                        uint4 e;
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
+                                     : "r"(ray_slab + 16u * (unsigned) s));
+                        gvl = __longlong_as_double((long long) (((unsigned long long) e.y << 32) | e.x));
+                        const float *row = reinterpret_cast<const float *>(((unsigned long long) e.w << 32) | e.z);
+#pragma unroll
+                        for (int q = 0; q < KS; q++)
+                            g[q] = __ldg(row + koff[q]);
+                    };
+                    if (lo < hi) {
+                        // the row of the next record is requested before the current one is added
+                        double gvlA, gvlB;
+                        float gA[KS], gB[KS];
+                        fetch(lo, gvlA, gA);
+                        for (int s = lo;; s += 2) {
+                            fetch(min(s + 1, hi - 1), gvlB, gB);
+#pragma unroll
+                            for (int q = 0; q < KS; q++)
+                                gl[q] = __fma_rn(gvlA, (double) gA[q], gl[q]);
+                            if (s + 1 >= hi)
+                                break;
+                            fetch(min(s + 2, hi - 1), gvlA, gA);
+#pragma unroll
+                            for (int q = 0; q < KS; q++)
+                                gl[q] = __fma_rn(gvlB, (double) gB[q], gl[q]);
+                            if (s + 2 >= hi)
+                                break;
+                        }
+                    }
+                    double Iv[KS];
+                    bool neg = false, nan = false;
+#pragma unroll
+                    for (int q = 0; q < KS; q++) {
+                        Iv[q] = __dmul_rn(f, seedv[q]) * exp_any(gl[q], KC);
+                        neg = neg || (live[q] && Iv[q] < 0.0);
+                        nan = nan || (live[q] && Iv[q] != Iv[q]);
+                    }
+                    const bool any_neg = __any_sync(0xffffffffu, neg);
+                    const bool any_nan = __any_sync(0xffffffffu, nan);
+                    if (any_neg || any_nan) { // negative (2) wins over NaN (3)
+                        if (lane == 0) {
+                            float rx, ry, ra, rb;
+                            int pi, pj, ka, m;
+                            seeded_slot_ray(P, c, (long long) base + j, rx, ry, ra, rb, pi, pj, ka, m);
+                            report_failure(o.fail, any_neg ? 2 : 3, rx, ry, ra, rb);
+                        }
+                        continue;
+                    }
+                    // ---- binning: run-length combined in registers ----
+                    if (pix != cur_pix) {
+                        flush_pix();
+                        cur_pix = pix;
+                    }
+                    if (bin != cur_bin) { // one warp reduction per run of rays with the same bin
+                        flush_bin();
+                        cur_bin = bin;
+                    }
+#pragma unroll
+                    for (int q = 0; q < KS; q++) {
+                        acc_w = __fma_rn(dv2[q], Iv[q], acc_w);
+                        acc[q] = __fma_rn(Iv[q], P.scale, acc[q]);
+                    }
+                }
+            }
+        }
+        flush_pix();
+        flush_bin();
+    }
+}
+
 // Trajectory intensities of RayTrace::calc_ray_path (RAY_DEBUG path of RayTrace_calc_ray,
 // :536-566): one warp per explicit ray, lane = frequency bin, K <= 128.  With a debug buffer the
 // reference always integrates emission-style (:543), over ALL (segment, sub-segment) records in
@@ -1603,6 +1852,20 @@ void launch_integrate_scatter(const DevProblem &P, const Chunk &c, bool list_mod
         blocks = cap;
     const int ks = std::min(4, (P.K + 31) / 32);
     const size_t smem = 8 * RTB_SLAB_RECORDS * sizeof(uint4) + sizeof(float *) * (size_t) P.N;
+    const int S = (P.N - 1) * RTB_N_SUB;
+#ifndef RTB_NO_SEEDED_KERNEL
+    // the seeded image of create_image: the lean kernel
+    if (!list_mode && P.use_emis == 0 && o.image && o.I_ang && !o.Iv && !o.error && P.K <= 32 * ks && S >= 1 &&
+        S <= RTB_SLAB_RECORDS) {
+        switch (ks) {
+        case 1: integrate_seeded_kernel<1><<<(unsigned) blocks, threads, smem, st>>>(P, c, h, o); break;
+        case 2: integrate_seeded_kernel<2><<<(unsigned) blocks, threads, smem, st>>>(P, c, h, o); break;
+        case 3: integrate_seeded_kernel<3><<<(unsigned) blocks, threads, smem, st>>>(P, c, h, o); break;
+        default: integrate_seeded_kernel<4><<<(unsigned) blocks, threads, smem, st>>>(P, c, h, o); break;
+        }
+        return;
+    }
+#endif
 #define RTB_LAUNCH_SCATTER(KS_)                                                                  \
     do {                                                                                         \
         if (list_mode)                                                                           \
