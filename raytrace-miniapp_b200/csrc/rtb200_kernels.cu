@@ -1524,10 +1524,15 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double exp_tab[RTB_EXP_TABLE_SIZE];
+    __shared__ double s_seed[128], s_dv2[128]; // seed spectrum and 2 dv per bin (zero past the last bin)
     uint4 *rec_slab = reinterpret_cast<uint4 *>(smem_raw);
     const float **s_gv = reinterpret_cast<const float **>(smem_raw + 8 * RTB_SLAB_RECORDS * sizeof(uint4)); // [N]
     for (int i = threadIdx.x; i < P.N; i += blockDim.x)
         s_gv[i] = P.planes[i].gv;
+    for (int k = threadIdx.x; k < 128; k += blockDim.x) {
+        s_seed[k] = k < P.K ? __ldg(&P.seed_fv[k]) : 0.0;
+        s_dv2[k] = k < P.K ? __ldg(&P.dv2[k]) : 0.0;
+    }
     load_exp_table(exp_tab); // includes __syncthreads()
     const ArrayConsts KC{ P.kfp, exp_tab };
     const int lane = threadIdx.x & 31;
@@ -1542,16 +1547,22 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
     // this lane's bins: k = lane + 32 q; lanes past the last bin shadow bin K-1 with a zero seed
     int koff[KS];
     bool live[KS];
-    double seedv[KS], dv2[KS], acc[KS];
+    double acc[KS];
 #pragma unroll
     for (int q = 0; q < KS; q++) {
         const int k = lane + 32 * q;
         live[q] = k < K;
         koff[q] = min(k, K - 1);
-        seedv[q] = live[q] ? __ldg(&P.seed_fv[k]) : 0.0;
-        dv2[q] = live[q] ? __ldg(&P.dv2[k]) : 0.0;
         acc[q] = 0.0;
     }
+    // (per-bin constants are re-read from shared memory per ray: cheaper than the registers)
+    const unsigned tab_seed = uniform_u32((unsigned) __cvta_generic_to_shared(s_seed)) + 8u * (unsigned) lane;
+    const unsigned tab_dv2 = uniform_u32((unsigned) __cvta_generic_to_shared(s_dv2)) + 8u * (unsigned) lane;
+    auto lds64 = [](unsigned a) {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+        return v;
+    };
     double acc_w = 0.0;
     int cur_pix = -1, cur_bin = -1; // (warp-uniform)
     auto flush_pix = [&]() {
@@ -1695,17 +1706,33 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
                                 break;
                         }
                     }
+                    // exp: one range test for all the ray's bins (|gl| >= 700, inf, NaN take the
+                    // library routine), so the KS evaluations run side by side without branches
                     double Iv[KS];
-                    bool neg = false, nan = false;
+                    bool in_range = true;
 #pragma unroll
-                    for (int q = 0; q < KS; q++) {
-                        Iv[q] = __dmul_rn(f, seedv[q]) * exp_any(gl[q], KC);
-                        neg = neg || (live[q] && Iv[q] < 0.0);
-                        nan = nan || (live[q] && Iv[q] != Iv[q]);
+                    for (int q = 0; q < KS; q++)
+                        in_range = in_range && fabs(gl[q]) < 700.0;
+                    if (__all_sync(0xffffffffu, in_range)) {
+#pragma unroll
+                        for (int q = 0; q < KS; q++)
+                            Iv[q] = __dmul_rn(f, lds64(tab_seed + 256u * q)) * exp_core(gl[q], KC);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < KS; q++)
+                            Iv[q] = __dmul_rn(f, lds64(tab_seed + 256u * q)) * exp_any(gl[q], KC);
                     }
-                    const bool any_neg = __any_sync(0xffffffffu, neg);
-                    const bool any_nan = __any_sync(0xffffffffu, nan);
-                    if (any_neg || any_nan) { // negative (2) wins over NaN (3)
+                    // failed ray: negative (code 2) or NaN (code 3) intensity in a live bin
+                    bool bad = false;
+#pragma unroll
+                    for (int q = 0; q < KS; q++)
+                        bad = bad || (live[q] && !(Iv[q] >= 0.0));
+                    if (__any_sync(0xffffffffu, bad)) {
+                        bool neg = false;
+#pragma unroll
+                        for (int q = 0; q < KS; q++)
+                            neg = neg || (live[q] && Iv[q] < 0.0);
+                        const bool any_neg = __any_sync(0xffffffffu, neg); // negative (2) wins over NaN (3)
                         if (lane == 0) {
                             float rx, ry, ra, rb;
                             int pi, pj, ka, m;
@@ -1725,7 +1752,7 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
                     }
 #pragma unroll
                     for (int q = 0; q < KS; q++) {
-                        acc_w = __fma_rn(dv2[q], Iv[q], acc_w);
+                        acc_w = __fma_rn(lds64(tab_dv2 + 256u * q), Iv[q], acc_w);
                         acc[q] = __fma_rn(Iv[q], P.scale, acc[q]);
                     }
                 }
