@@ -1526,15 +1526,18 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
     __shared__ double exp_tab[RTB_EXP_TABLE_SIZE];
     __shared__ double s_seed[128], s_dv2[128]; // seed spectrum and 2 dv per bin (zero past the last bin)
     uint4 *rec_slab = reinterpret_cast<uint4 *>(smem_raw);
-    const float **s_gv = reinterpret_cast<const float **>(smem_raw + 8 * RTB_SLAB_RECORDS * sizeof(uint4)); // [N]
+    // the lineshape tables in double (DevPlane::gvd: packed for every gain-only problem)
+    const double **s_gv = reinterpret_cast<const double **>(smem_raw + 8 * RTB_SLAB_RECORDS * sizeof(uint4)); // [N]
     for (int i = threadIdx.x; i < P.N; i += blockDim.x)
-        s_gv[i] = P.planes[i].gv;
+        s_gv[i] = P.planes[i].gvd;
     for (int k = threadIdx.x; k < 128; k += blockDim.x) {
         s_seed[k] = k < P.K ? __ldg(&P.seed_fv[k]) : 0.0;
         s_dv2[k] = k < P.K ? __ldg(&P.dv2[k]) : 0.0;
     }
     load_exp_table(exp_tab); // includes __syncthreads()
-    const ArrayConsts KC{ P.kfp, exp_tab };
+    // (constants of exp pinned like in the owner kernel: uniform registers instead of four
+    // constant-bank loads and a rebuilt shared-memory window per ray)
+    const PinnedConsts KC(P.kfp_g, exp_tab);
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = (int) uniform_u32(threadIdx.x >> 5);
     const unsigned slab = uniform_u32((unsigned) __cvta_generic_to_shared(rec_slab + warp_in_cta * RTB_SLAB_RECORDS));
@@ -1645,7 +1648,7 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
                     for (int r = lane; r < nrec; r += 32) {
                         const int4 rv = __ldg(reinterpret_cast<const int4 *>(&src[r]));
                         const int sg = r % S;
-                        const float *row = s_gv[sg / RTB_N_SUB + 1] + (size_t) rv.z * K;
+                        const double *row = s_gv[sg / RTB_N_SUB + 1] + (size_t) rv.z * K;
                         const unsigned long long ra = reinterpret_cast<unsigned long long>(row);
                         const unsigned long long gd =
                             (unsigned long long) __double_as_longlong((double) __int_as_float(rv.x));
@@ -1675,13 +1678,13 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
 #pragma unroll
                     for (int q = 0; q < KS; q++)
                         gl[q] = 0.0;
-                    auto fetch = [&](int s, double &gvl, float (&g)[KS]) {
+                    auto fetch = [&](int s, double &gvl, double (&g)[KS]) {
                         uint4 e;
                         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                                      : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
                                      : "r"(ray_slab + 16u * (unsigned) s));
                         gvl = __longlong_as_double((long long) (((unsigned long long) e.y << 32) | e.x));
-                        const float *row = reinterpret_cast<const float *>(((unsigned long long) e.w << 32) | e.z);
+                        const double *row = reinterpret_cast<const double *>(((unsigned long long) e.w << 32) | e.z);
 #pragma unroll
                         for (int q = 0; q < KS; q++)
                             g[q] = __ldg(row + koff[q]);
@@ -1689,19 +1692,19 @@ __global__ void __launch_bounds__(256, RTB_SCATTER_MINBLOCKS)
                     if (lo < hi) {
                         // the row of the next record is requested before the current one is added
                         double gvlA, gvlB;
-                        float gA[KS], gB[KS];
+                        double gA[KS], gB[KS];
                         fetch(lo, gvlA, gA);
                         for (int s = lo;; s += 2) {
                             fetch(min(s + 1, hi - 1), gvlB, gB);
 #pragma unroll
                             for (int q = 0; q < KS; q++)
-                                gl[q] = __fma_rn(gvlA, (double) gA[q], gl[q]);
+                                gl[q] = __fma_rn(gvlA, gA[q], gl[q]);
                             if (s + 1 >= hi)
                                 break;
                             fetch(min(s + 2, hi - 1), gvlA, gA);
 #pragma unroll
                             for (int q = 0; q < KS; q++)
-                                gl[q] = __fma_rn(gvlB, (double) gB[q], gl[q]);
+                                gl[q] = __fma_rn(gvlB, gB[q], gl[q]);
                             if (s + 2 >= hi)
                                 break;
                         }

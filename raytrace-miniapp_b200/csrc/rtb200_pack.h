@@ -277,6 +277,18 @@ inline unsigned copy_abs_max(float *dst, const float *src, size_t n, unsigned m0
     return m;
 }
 
+// float -> double, on host threads for large tables
+inline void widen_floats(double *dst, const float *src, size_t n)
+{
+    parallel_pieces(n, n * sizeof(double), [dst, src](unsigned, size_t a, size_t b) {
+        for (size_t i = a; i < b; i++)
+            dst[i] = (double) ld_u(&src[i]);
+    });
+}
+
+// RayTraceImageHelper.h:402: emission + gain (ASE) unless a seed is given
+inline bool problem_use_emis(const rtb200_problem &p) { return p.gain[0].E0 != nullptr && p.seed == nullptr; }
+
 // Bump allocator over the staging blob.  With host == nullptr it only measures.
 class Blob {
 public:
@@ -328,7 +340,7 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
     out.K = K;
     out.dz0 = (float) e.dz;
     out.c = 0.5f;
-    out.use_emis = (p.gain[0].E0 != nullptr && p.seed == nullptr) ? 1 : 0; // :402
+    out.use_emis = problem_use_emis(p) ? 1 : 0; // :402
     const double kfp[RTB_K_COUNT] = { RTB_K_VALUES };
     std::memcpy(out.kfp, kfp, sizeof(kfp));
 
@@ -349,6 +361,8 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
         double *y = blob.alloc<double>((size_t) g.Ny, &P.y);
         Node *node = blob.alloc<Node>(nn, &P.node);
         float *gv = (gvb ? gv_blob : blob).alloc<float>(nn * (size_t) K, &P.gv);
+        // gain-only problems: the table once more in double (DevPlane::gvd)
+        double *gvd = out.use_emis ? nullptr : (gvb ? gv_blob : blob).alloc<double>(nn * (size_t) K, &P.gvd);
         if (gvb)
             gvb->bytes = gv_blob.size();
         AxisCell *cx = blob.alloc<AxisCell>((size_t) g.Nx, &P.cx);
@@ -389,6 +403,8 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
             });
             if (gv && (!gvb || gvb->copy)) {
                 gv_absmax = copy_abs_max(gv, g.gv, nn * (size_t) K, gv_absmax);
+                if (gvd)
+                    widen_floats(gvd, g.gv, nn * (size_t) K);
             } else {
                 gv_absmax = 0x7fffffffu; // tables filled later: pack_gv() returns the value
             }
@@ -568,6 +584,10 @@ inline unsigned pack_gv(const rtb200_problem &p, char *host)
         const float *unused;
         float *gv = gv_blob.alloc<float>(n, &unused);
         m = copy_abs_max(gv, g.gv, n, m);
+        if (!problem_use_emis(p)) { // same layout as pack_problem
+            const double *unused_d;
+            widen_floats(gv_blob.alloc<double>(n, &unused_d), g.gv, n);
+        }
     }
     return m;
 }
