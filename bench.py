@@ -456,6 +456,33 @@ def run_gpu(args):
         elif args.scaling == "weak":  # N = 1: the fixed image IS the workload
             line["strong"] = {"workload": name, "image_time_ms_device": ms_per_step,
                               "image_time_ms_e2e": e2e_s * 1e3, "speedup_vs_1": 1.0, "speedup_vs_1_e2e": 1.0}
+        if world == 1:
+            # The seeded half of BASELINE.json's config 2 (seed_small.dat: 7 803 000 rays, gain-only
+            # integration binned by the exit ray), timed the same way as the headline; parity
+            # against the unmodified reference's own CPU output (tests/golden, tools/make_golden.py).
+            try:
+                from raytrace_miniapp_b200 import problem_io
+                sp, extra = problem_io.load_npz(os.path.join(ROOT, "tests", "golden", "seed_small.npz"))
+                sjob = Job(sp, rl.Context(local), sharded=False)
+                ks = max(3, min(K, 10))
+                stm = sjob.timed(ks, 3)
+                s_seg = sp.n_rays * (sp.N - 1) * 3
+                ref_img = torch.from_numpy(extra["ref_cpu_image"]).to(dev).flatten()
+                ref_ang = torch.from_numpy(extra["ref_cpu_I_ang"]).to(dev).flatten()
+                rel = lambda a, b: float((torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(b)).cpu())  # noqa: E731
+                line["seeded"] = {
+                    "workload": "seed_small.dat (seed beam %dx%dx%dx%d = %d rays, N=%d planes, nv=%d)" % (
+                        sp.seed_beam.nx, sp.seed_beam.ny, sp.seed_beam.na, sp.seed_beam.nb, sp.n_rays, sp.N,
+                        sp.euv_beam.nv),
+                    "rays": sp.n_rays, "ray_segments": s_seg, "steps": ks,
+                    "image_time_ms_device": stm["ms_per_step"],
+                    "kernel_ms_per_step": {"march": stm["march_ms"], "integrate": stm["integrate_ms"]},
+                    "value": s_seg / (stm["ms_per_step"] * 1e-3), "unit": "ray-segments/s",
+                    "parity": {"checked": "image / I_ang against the reference's own CPU result (tests/golden)",
+                               "image_relL2": rel(sjob.image, ref_img), "I_ang_relL2": rel(sjob.I_ang, ref_ang)}}
+                sjob.ctx.close()
+            except Exception as ex:  # informative; never lose the headline line
+                line["seeded"] = {"error": str(ex)[-300:]}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 r = reference_cpu(problem, args.cpu_stride or 16, 1, 0)

@@ -99,6 +99,7 @@ struct rtb200_ctx {
     // staging
     PinBuf h_blob, h_gv;
     DevBuf<char> d_blob, d_gv; // d_gv: the lineshape tables (read by the integration only)
+    DevBuf<char> d_cells;      // per-cell records, derived on the device (CellBlob, rtb200_pack.h)
     const rtb200_problem *gv_pending = nullptr; // tables not filled/uploaded yet (create_image)
     size_t gv_bytes = 0;
     DevProblem prob;
@@ -318,15 +319,18 @@ int stage_impl(rtb200_ctx *ctx, const rtb200_problem *p, bool explicit_rays, int
     }
     DevProblem tmp;
     GvBlob gvb{ nullptr, nullptr, false, 0 };
-    const size_t bytes = pack_problem(*p, explicit_rays, method, scale, nullptr, nullptr, tmp, &gvb);
+    CellBlob cellb{ nullptr, 0 };
+    const size_t bytes = pack_problem(*p, explicit_rays, method, scale, nullptr, nullptr, tmp, &gvb, &cellb);
     RTB_CUDA(ctx->h_blob.reserve(bytes));
     RTB_CUDA(ctx->d_blob.reserve(bytes));
     RTB_CUDA(ctx->h_gv.reserve(gvb.bytes));
     RTB_CUDA(ctx->d_gv.reserve(gvb.bytes));
+    RTB_CUDA(ctx->d_cells.reserve(cellb.bytes));
     gvb.host = ctx->h_gv.p;
     gvb.dev = ctx->d_gv.p;
     gvb.copy = !defer_gv;
-    pack_problem(*p, explicit_rays, method, scale, ctx->h_blob.p, ctx->d_blob.p, ctx->prob, &gvb);
+    cellb.dev = ctx->d_cells.p;
+    pack_problem(*p, explicit_rays, method, scale, ctx->h_blob.p, ctx->d_blob.p, ctx->prob, &gvb, &cellb);
     ctx->gv_bytes = gvb.bytes;
     ctx->gv_pending = defer_gv ? p : nullptr;
     if (ctx->ieee_div) {
@@ -341,6 +345,12 @@ int stage_impl(rtb200_ctx *ctx, const rtb200_problem *p, bool explicit_rays, int
     RTB_CUDA(cudaMemsetAsync(ctx->d_fail, 0, sizeof(FailState), ctx->stream));
     RTB_CUDA(cudaMemcpyAsync(ctx->d_blob.p, ctx->h_blob.p, bytes, cudaMemcpyHostToDevice,
                              ctx->stream));
+    {
+        long long max_nodes = 0;
+        for (int i = 0; i < p->N; i++)
+            max_nodes = std::max(max_nodes, (long long) p->gain[i].Nx * p->gain[i].Ny);
+        launch_build_cell_records(ctx->prob.planes, ctx->prob.N, max_nodes, ctx->stream);
+    }
     if (!defer_gv)
         RTB_CUDA(cudaMemcpyAsync(ctx->d_gv.p, ctx->h_gv.p, gvb.bytes, cudaMemcpyHostToDevice,
                                  ctx->stream));
@@ -539,6 +549,7 @@ void rtb200_destroy(rtb200_ctx *ctx)
     ctx->d_blob.release();
     ctx->h_gv.release();
     ctx->d_gv.release();
+    ctx->d_cells.release();
     ctx->d_seg.release();
     ctx->d_meta.release();
     ctx->d_exit.release();

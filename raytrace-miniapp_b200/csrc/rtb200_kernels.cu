@@ -2028,6 +2028,58 @@ void launch_fdiv_check(unsigned b_first, unsigned b_count, int ea, int eb, int v
     fdiv_check_kernel<<<148 * 16, 256, 0, st>>>(b_first, b_count, ea, eb, variant, out);
 }
 
+// ------------------------------------------------------------------------------------------
+// Cell records (CellRec) of every plane, derived on the device: record i1 = (k1-1) + (k2-1)*Nx
+// holds the corners i1, i1+1, i1+Nx, i1+Nx+1 in the reference's order
+// (RayTraceImageHelper.h:474-477) - the float corner values, their four double differences
+// (:333-334) and the cell's copy of the two axis intervals.  One thread per node index; the last
+// row and column are never addressed (zero).  Same IEEE operations as fill_cell_records.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) build_cell_records_kernel(const DevPlane *planes)
+{
+    const DevPlane &D = planes[blockIdx.y];
+    const int Nx = D.Nx, Ny = D.Ny;
+    const long long i1 = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i1 >= (long long) Nx * Ny)
+        return;
+    const int j = (int) (i1 / Nx), i = (int) (i1 - (long long) j * Nx);
+    CellRec r;
+    if (i + 1 >= Nx || j + 1 >= Ny) {
+        memset(&r, 0, sizeof(r));
+    } else {
+        const long long c[4] = { i1, i1 + 1, i1 + Nx, i1 + Nx + 1 };
+        double nc[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const Node nd = load_node(&D.node[c[q]]);
+            nc[q] = nd.n;
+            r.nf[q] = __double2float_rn(nd.n);
+            r.g0[q] = nd.g0;
+            r.E0[q] = nd.E0;
+        }
+        r.n10 = __dsub_rn(nc[1], nc[0]);
+        r.n32 = __dsub_rn(nc[3], nc[2]);
+        r.n20 = __dsub_rn(nc[2], nc[0]);
+        r.n31 = __dsub_rn(nc[3], nc[1]);
+        const AxisCell &ax = D.cx[i + 1], &ay = D.cy[j + 1];
+        r.xl = ax.lo;
+        r.dxd = ax.dd;
+        r.rdx = ax.rd;
+        r.yl = ay.lo;
+        r.dyd = ay.dd;
+        r.rdy = ay.rd;
+    }
+    const_cast<CellRec *>(D.cell)[i1] = r;
+}
+
+void launch_build_cell_records(const DevPlane *planes, int N, long long max_nodes, cudaStream_t st)
+{
+    if (N <= 0 || max_nodes <= 0)
+        return;
+    const dim3 grid((unsigned) ((max_nodes + 255) / 256), (unsigned) N);
+    build_cell_records_kernel<<<grid, 256, 0, st>>>(planes);
+}
+
 void launch_fp64_peak(double *out, int iters, cudaStream_t st, int *blocks, int *threads)
 {
     *blocks = 148 * 8;

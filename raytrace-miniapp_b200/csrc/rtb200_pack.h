@@ -322,16 +322,27 @@ struct GvBlob {
     size_t bytes;
 };
 
+// The per-cell records (CellRec) are derived data, a third of the main blob: the product lays them
+// out in a device buffer of their own and lets a small kernel derive them from the uploaded nodes
+// and interval tables (build_cell_records_kernel: the same IEEE operations as fill_cell_records),
+// so the host neither computes nor uploads them.  Without a CellBlob (host builds of the march:
+// tests/hostsim) they stay in the main blob and are filled here.
+struct CellBlob {
+    const char *dev;
+    size_t bytes;
+};
+
 // Packs `p` into the blob.  Returns the number of bytes used; fills `out` (pointers relative
 // to dev_base).  explicit_rays: the ray list comes separately (rtb200_trace_rays), so only the
 // planes, the destination grid and dv are packed and method/scale are given by the caller.
 // gvb == nullptr keeps the lineshape tables inside the main blob.
 inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int method_in,
                            double scale_in, char *host, const char *dev_base, DevProblem &out,
-                           GvBlob *gvb = nullptr)
+                           GvBlob *gvb = nullptr, CellBlob *cellb = nullptr)
 {
     Blob blob(host, dev_base);
     Blob gv_blob(gvb ? gvb->host : nullptr, gvb ? gvb->dev : nullptr);
+    Blob cell_blob(nullptr, cellb ? cellb->dev : nullptr);
     const bool fill = blob.filling();
     const rtb200_beam &e = *p.euv_beam;
     const int N = p.N, K = e.nv;
@@ -367,7 +378,9 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
             gvb->bytes = gv_blob.size();
         AxisCell *cx = blob.alloc<AxisCell>((size_t) g.Nx, &P.cx);
         AxisCell *cy = blob.alloc<AxisCell>((size_t) g.Ny, &P.cy);
-        CellRec *cell = blob.alloc<CellRec>(nn, &P.cell);
+        CellRec *cell = cellb ? cell_blob.alloc<CellRec>(nn, &P.cell) : blob.alloc<CellRec>(nn, &P.cell);
+        if (cellb)
+            cellb->bytes = cell_blob.size();
         if (fill) {
             bool ok = true;
             double last_w = 0.0;
@@ -390,7 +403,8 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
             recip(g.y, g.Ny);
             fill_axis_cells(g.x, g.Nx, cx);
             fill_axis_cells(g.y, g.Ny, cy);
-            fill_cell_records(g, cx, cy, cell);
+            if (cell) // (null: derived on the device)
+                fill_cell_records(g, cx, cy, cell);
             P.fast_div = ok ? 1 : 0;
             std::memcpy(x, g.x, sizeof(double) * g.Nx);
             std::memcpy(y, g.y, sizeof(double) * g.Ny);

@@ -250,3 +250,22 @@ long long hostsim_check_rsqrt_identity(unsigned lo_bits, unsigned hi_bits)
 }
 
 } // extern "C"
+
+// Timing door (tools): seconds per packing pass of the main blob, lineshape tables deferred as
+// rtb200_create_image does (they are packed while the march runs).
+#include <chrono>
+extern "C" double hostsim_pack_seconds(const rtb200_problem *p, int reps)
+{
+    DevProblem P;
+    GvBlob gm{ nullptr, nullptr, false, 0 };
+    const size_t bytes = pack_problem(*p, false, 0, 0.0, nullptr, nullptr, P, &gm);
+    std::vector<char> blob(bytes + 256), gvh(gm.bytes + 256);
+    char *base = (char *) (((uintptr_t) blob.data() + 255) & ~(uintptr_t) 255);
+    char *gbase = (char *) (((uintptr_t) gvh.data() + 255) & ~(uintptr_t) 255);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < reps; i++) {
+        GvBlob g{ gbase, gbase, false, 0 };
+        pack_problem(*p, false, 0, 0.0, base, base, P, &g);
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / reps;
+}
