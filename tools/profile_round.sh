@@ -14,7 +14,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:"march_flat|integrate_ase_owner" -s 2 -c 2 \
     -o gpurun_out/${TAG}_full -f python tools/time_cases.py ASE_medium-synth > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -1 gpurun_out/${TAG}_ncu_full.log
-ncu --set full --clock-control none --import-source on -k regex:"march_flat|integrate_scatter" -s 2 -c 2 \
+ncu --set full --clock-control none --import-source on -k regex:"march_flat|integrate_seeded|integrate_scatter" -s 2 -c 2 \
     -o gpurun_out/${TAG}_seed -f python tools/time_cases.py seed_small > gpurun_out/${TAG}_ncu_seed.log 2>&1
 tail -1 gpurun_out/${TAG}_ncu_seed.log
 python tools/run_configs.py > gpurun_out/${TAG}_configs.json 2> gpurun_out/${TAG}_configs.err
