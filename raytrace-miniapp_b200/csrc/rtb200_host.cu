@@ -100,6 +100,7 @@ struct rtb200_ctx {
     PinBuf h_blob, h_gv;
     DevBuf<char> d_blob, d_gv; // d_gv: the lineshape tables (read by the integration only)
     DevBuf<char> d_cells;      // per-cell records, derived on the device (CellBlob, rtb200_pack.h)
+    DevBuf<char> d_gvd;        // lineshape tables in double (gain-only problems), widened on the device
     const rtb200_problem *gv_pending = nullptr; // tables not filled/uploaded yet (create_image)
     size_t gv_bytes = 0;
     DevProblem prob;
@@ -298,6 +299,10 @@ int flush_gv(rtb200_ctx *ctx, cudaStream_t st)
     // finished before its results were read back.)
     RTB_CUDA(cudaMemcpyAsync(ctx->d_gv.p, ctx->h_gv.p, ctx->gv_bytes, cudaMemcpyHostToDevice,
                              ctx->copy_stream));
+    if (!ctx->prob.use_emis) { // (the plane descriptors were uploaded on ctx->stream: stage_done)
+        RTB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_done, 0));
+        launch_widen_gv(ctx->prob.planes, ctx->prob.N, ctx->prob.K, ctx->copy_stream);
+    }
     RTB_CUDA(cudaEventRecord(ctx->gv_ready, ctx->copy_stream));
     RTB_CUDA(cudaStreamWaitEvent(st, ctx->gv_ready, 0));
     return RTB200_OK;
@@ -319,18 +324,20 @@ int stage_impl(rtb200_ctx *ctx, const rtb200_problem *p, bool explicit_rays, int
     }
     DevProblem tmp;
     GvBlob gvb{ nullptr, nullptr, false, 0 };
-    CellBlob cellb{ nullptr, 0 };
-    const size_t bytes = pack_problem(*p, explicit_rays, method, scale, nullptr, nullptr, tmp, &gvb, &cellb);
+    CellBlob cellb{ nullptr, 0 }, gvdb{ nullptr, 0 };
+    const size_t bytes = pack_problem(*p, explicit_rays, method, scale, nullptr, nullptr, tmp, &gvb, &cellb, &gvdb);
     RTB_CUDA(ctx->h_blob.reserve(bytes));
     RTB_CUDA(ctx->d_blob.reserve(bytes));
     RTB_CUDA(ctx->h_gv.reserve(gvb.bytes));
     RTB_CUDA(ctx->d_gv.reserve(gvb.bytes));
     RTB_CUDA(ctx->d_cells.reserve(cellb.bytes));
+    RTB_CUDA(ctx->d_gvd.reserve(gvdb.bytes));
+    gvdb.dev = ctx->d_gvd.p;
     gvb.host = ctx->h_gv.p;
     gvb.dev = ctx->d_gv.p;
     gvb.copy = !defer_gv;
     cellb.dev = ctx->d_cells.p;
-    pack_problem(*p, explicit_rays, method, scale, ctx->h_blob.p, ctx->d_blob.p, ctx->prob, &gvb, &cellb);
+    pack_problem(*p, explicit_rays, method, scale, ctx->h_blob.p, ctx->d_blob.p, ctx->prob, &gvb, &cellb, &gvdb);
     ctx->gv_bytes = gvb.bytes;
     ctx->gv_pending = defer_gv ? p : nullptr;
     if (ctx->ieee_div) {
@@ -351,9 +358,12 @@ int stage_impl(rtb200_ctx *ctx, const rtb200_problem *p, bool explicit_rays, int
             max_nodes = std::max(max_nodes, (long long) p->gain[i].Nx * p->gain[i].Ny);
         launch_build_cell_records(ctx->prob.planes, ctx->prob.N, max_nodes, ctx->stream);
     }
-    if (!defer_gv)
+    if (!defer_gv) {
         RTB_CUDA(cudaMemcpyAsync(ctx->d_gv.p, ctx->h_gv.p, gvb.bytes, cudaMemcpyHostToDevice,
                                  ctx->stream));
+        if (!ctx->prob.use_emis)
+            launch_widen_gv(ctx->prob.planes, ctx->prob.N, ctx->prob.K, ctx->stream);
+    }
     ctx->ev_h2d.second = new_event(ctx, ctx->stream);
     RTB_CUDA(cudaEventRecord(ctx->stage_done, ctx->stream));
     ctx->have_h2d = true;
@@ -550,6 +560,7 @@ void rtb200_destroy(rtb200_ctx *ctx)
     ctx->h_gv.release();
     ctx->d_gv.release();
     ctx->d_cells.release();
+    ctx->d_gvd.release();
     ctx->d_seg.release();
     ctx->d_meta.release();
     ctx->d_exit.release();

@@ -2086,6 +2086,25 @@ void launch_build_cell_records(const DevPlane *planes, int N, long long max_node
     build_cell_records_kernel<<<grid, 256, 0, st>>>(planes);
 }
 
+// The lineshape tables of a gain-only problem once more in double (the seeded kernel's operand
+// type): widened on the device from the uploaded float tables, so the host neither converts nor
+// uploads them.
+__global__ void __launch_bounds__(256) widen_gv_kernel(const DevPlane *planes, int K)
+{
+    const DevPlane &D = planes[blockIdx.y];
+    const size_t n = (size_t) D.Nx * D.Ny * (size_t) K;
+    double *dst = const_cast<double *>(D.gvd);
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+        dst[i] = (double) __ldg(&D.gv[i]);
+}
+
+void launch_widen_gv(const DevPlane *planes, int N, int K, cudaStream_t st)
+{
+    if (N <= 0 || K <= 0)
+        return;
+    widen_gv_kernel<<<dim3(148 * 2, (unsigned) N), 256, 0, st>>>(planes, K);
+}
+
 void launch_fp64_peak(double *out, int iters, cudaStream_t st, int *blocks, int *threads)
 {
     *blocks = 148 * 8;

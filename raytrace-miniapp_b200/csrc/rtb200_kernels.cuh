@@ -60,6 +60,8 @@ void launch_path_intensity(const DevProblem &P, const Chunk &c, const Handoff &h
 // Derives the per-cell records of every plane from the uploaded nodes and interval tables
 // (what rtb200_pack.h's fill_cell_records does on the host, operation for operation).
 void launch_build_cell_records(const DevPlane *planes, int N, long long max_nodes, cudaStream_t st);
+// Gain-only problems: DevPlane::gvd[i] = (double) DevPlane::gv[i] for every plane (K bins per node).
+void launch_widen_gv(const DevPlane *planes, int N, int K, cudaStream_t st);
 void launch_fp64_peak(double *out, int iters, cudaStream_t st, int *blocks, int *threads);
 void launch_fdiv_check(unsigned b_first, unsigned b_count, int ea, int eb, int variant,
                        unsigned long long *out, cudaStream_t st);

@@ -338,11 +338,14 @@ struct CellBlob {
 // gvb == nullptr keeps the lineshape tables inside the main blob.
 inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int method_in,
                            double scale_in, char *host, const char *dev_base, DevProblem &out,
-                           GvBlob *gvb = nullptr, CellBlob *cellb = nullptr)
+                           GvBlob *gvb = nullptr, CellBlob *cellb = nullptr, CellBlob *gvdb = nullptr)
 {
+    // gvdb: like cellb for the double copy of the lineshape tables of gain-only problems
+    // (DevPlane::gvd): laid out in a device buffer of its own and widened there (widen_gv_kernel)
     Blob blob(host, dev_base);
     Blob gv_blob(gvb ? gvb->host : nullptr, gvb ? gvb->dev : nullptr);
     Blob cell_blob(nullptr, cellb ? cellb->dev : nullptr);
+    Blob gvd_blob(nullptr, gvdb ? gvdb->dev : nullptr);
     const bool fill = blob.filling();
     const rtb200_beam &e = *p.euv_beam;
     const int N = p.N, K = e.nv;
@@ -373,7 +376,15 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
         Node *node = blob.alloc<Node>(nn, &P.node);
         float *gv = (gvb ? gv_blob : blob).alloc<float>(nn * (size_t) K, &P.gv);
         // gain-only problems: the table once more in double (DevPlane::gvd)
-        double *gvd = out.use_emis ? nullptr : (gvb ? gv_blob : blob).alloc<double>(nn * (size_t) K, &P.gvd);
+        double *gvd = nullptr;
+        if (!out.use_emis) {
+            if (gvdb) {
+                gvd_blob.alloc<double>(nn * (size_t) K, &P.gvd);
+                gvdb->bytes = gvd_blob.size();
+            } else {
+                gvd = blob.alloc<double>(nn * (size_t) K, &P.gvd);
+            }
+        }
         if (gvb)
             gvb->bytes = gv_blob.size();
         AxisCell *cx = blob.alloc<AxisCell>((size_t) g.Nx, &P.cx);
@@ -415,10 +426,10 @@ inline size_t pack_problem(const rtb200_problem &p, bool explicit_rays, int meth
                     node[q].E0 = g.E0 ? ld_u(&g.E0[q]) : 0.0f;
                 }
             });
+            if (gvd) // (null: widened on the device)
+                widen_floats(gvd, g.gv, nn * (size_t) K);
             if (gv && (!gvb || gvb->copy)) {
                 gv_absmax = copy_abs_max(gv, g.gv, nn * (size_t) K, gv_absmax);
-                if (gvd)
-                    widen_floats(gvd, g.gv, nn * (size_t) K);
             } else {
                 gv_absmax = 0x7fffffffu; // tables filled later: pack_gv() returns the value
             }
@@ -598,10 +609,6 @@ inline unsigned pack_gv(const rtb200_problem &p, char *host)
         const float *unused;
         float *gv = gv_blob.alloc<float>(n, &unused);
         m = copy_abs_max(gv, g.gv, n, m);
-        if (!problem_use_emis(p)) { // same layout as pack_problem
-            const double *unused_d;
-            widen_floats(gv_blob.alloc<double>(n, &unused_d), g.gv, n);
-        }
     }
     return m;
 }

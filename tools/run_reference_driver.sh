@@ -8,4 +8,4 @@ B=./oracle/_ref/CreateImageB200_legacy
 nvidia-smi -L | wc -l
 $B -iterations=5 -methods=cpu,threads,Cuda,b200,b200-direct,b200-multigpu .bench_tmp/ASE_small.dat 2>&1 | grep -v "^$" | tail -10
 $B -iterations=5 -methods=threads,Cuda,b200,b200-direct,b200-multigpu .bench_tmp/ASE_medium_synth.dat 2>&1 | grep -v "^$" | tail -10
-$B -iterations=3 -methods=cpu,Cuda,b200,b200-direct,b200-multigpu .bench_tmp/seed_small.dat 2>&1 | grep -v "^$" | tail -13
+$B -iterations=3 -methods=${SEED_METHODS:-cpu,Cuda,b200,b200-direct,b200-multigpu} .bench_tmp/seed_small.dat 2>&1 | grep -v "^$" | tail -13
