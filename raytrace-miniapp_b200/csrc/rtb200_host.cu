@@ -101,6 +101,8 @@ struct rtb200_ctx {
     DevBuf<char> d_blob, d_gv; // d_gv: the lineshape tables (read by the integration only)
     DevBuf<char> d_cells;      // per-cell records, derived on the device (CellBlob, rtb200_pack.h)
     DevBuf<char> d_gvd;        // lineshape tables in double (gain-only problems), widened on the device
+    DevBuf<unsigned> d_pix_done; // per-pixel completion counts of the march (overlapped integration)
+    bool overlap = false;        // RTB200_OVERLAP=1: start the integration while the march drains
     const rtb200_problem *gv_pending = nullptr; // tables not filled/uploaded yet (create_image)
     size_t gv_bytes = 0;
     DevProblem prob;
@@ -420,8 +422,14 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
     int rc = ensure_handoff(ctx, pix_per_chunk * P.ab_max, need_exit);
     if (rc)
         return rc;
-    Handoff h{ ctx->d_seg.p, ctx->d_meta.p, need_exit ? ctx->d_exit.p : nullptr, nullptr };
+    Handoff h{ ctx->d_seg.p, ctx->d_meta.p, need_exit ? ctx->d_exit.p : nullptr, nullptr, nullptr };
     const bool owner = ctx->owner_ok && !out.Iv && !out.error;
+    // Overlapped form (owner kernel, lineshape tables already resident): the march counts the closed
+    // ray slots of every pixel, the integration is launched with programmatic stream serialization
+    // right behind it - nothing between the two launches - and each of its CTAs waits for its pixel.
+    const bool overlap = ctx->overlap && owner && !ctx->gv_pending;
+    if (overlap)
+        RTB_CUDA(ctx->d_pix_done.reserve((size_t) pix_per_chunk));
     for (long long a = pix0; a < pix1; a += pix_per_chunk) {
         Chunk c;
         std::memset(&c, 0, sizeof(c));
@@ -429,6 +437,21 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
         c.pix1 = std::min(pix1, a + pix_per_chunk);
         c.row_off = row_off;
         c.row_stride = row_stride;
+        if (overlap) {
+            RTB_CUDA(cudaMemsetAsync(ctx->d_pix_done.p, 0, sizeof(unsigned) * (size_t) (c.pix1 - c.pix0), st));
+            Handoff ho = h;
+            ho.pix_done = ctx->d_pix_done.p;
+            Outputs oo = out;
+            oo.pix_done = ctx->d_pix_done.p;
+            const size_t e0 = new_event(ctx, st);
+            launch_march(P, c, false, ho, ctx->d_fail, ctx->count_steps, st, ctx->d_work, ctx->march_blocks);
+            launch_integrate_ase_owner(P, c, ho, oo, st, true);
+            const size_t e2 = new_event(ctx, st);
+            ctx->ev_march.push_back({ e0, e2 }); // (the two kernels overlap: one interval)
+            ctx->ev_integ.push_back({ e2, e2 });
+            ctx->launches += 2;
+            continue;
+        }
         const size_t e0 = new_event(ctx, st);
         launch_march(P, c, false, h, ctx->d_fail, ctx->count_steps, st, ctx->d_work, ctx->march_blocks);
         const size_t e1m = new_event(ctx, st);
@@ -540,6 +563,8 @@ int rtb200_create(int device, rtb200_ctx **out)
         ctx->march_blocks = std::max(1, atoi(s));
     if (const char *s = getenv("RTB200_HANDOFF_MB"))
         ctx->handoff_bytes = (size_t) std::max(1, atoi(s)) << 20;
+    if (const char *s = getenv("RTB200_OVERLAP")) // start the integration while the march drains
+        ctx->overlap = atoi(s) != 0;
     if (const char *s = getenv("RTB200_COUNT_STEPS"))
         ctx->count_steps = atoi(s) != 0;
     if (const char *s = getenv("RTB200_IEEE_DIV")) // tests: plain IEEE divisions by the cell widths
@@ -561,6 +586,7 @@ void rtb200_destroy(rtb200_ctx *ctx)
     ctx->d_gv.release();
     ctx->d_cells.release();
     ctx->d_gvd.release();
+    ctx->d_pix_done.release();
     ctx->d_seg.release();
     ctx->d_meta.release();
     ctx->d_exit.release();

@@ -18,6 +18,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <cstring>
 #include <type_traits>
 
 #include "rtb200_fp64.cuh"
@@ -286,10 +287,15 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
             h.exit_ray[L] = e;
         }
         h.meta[L] = meta;
+        if (!LIST && h.pix_done) { // this ray's records and meta word first, then the count
+            __threadfence();
+            atomicAdd(&h.pix_done[L / (unsigned) P.ab_max], 1u);
+        }
         if (COUNT)
             total_steps += m.steps;
         pending = false;
     };
+    bool signalled = false; // (warp-uniform) dependents may be launched: this warp sees no more work
     for (;;) {
         const bool need = (m.st & (RTB_ST_PHASE | RTB_ST_DEAD)) == (unsigned) PH_DONE;
         const unsigned want = __ballot_sync(0xffffffffu, need);
@@ -311,6 +317,12 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
                 if (run_next >= n_slots)
                     exhausted = true;
             }
+            if (exhausted && !signalled) {
+                // the work queue is empty: the integration kernel may start filling the SMs that
+                // the march's last CTAs leave (it waits per pixel on Handoff::pix_done)
+                asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+                signalled = true;
+            }
             const unsigned mine = run_next + __popc(want & ((1u << lane) - 1u));
             const unsigned after = run_next + __popc(want);
             if (need && pending)
@@ -325,6 +337,10 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
                     const bool active = slot_source<LIST>(P, c, L, rx, ry, ra, rb, ta, tb);
                     if (!active) {
                         h.meta[L] = RTB_META_INACTIVE;
+                        if (!LIST && h.pix_done) {
+                            __threadfence();
+                            atomicAdd(&h.pix_done[L / (unsigned) P.ab_max], 1u);
+                        }
                     } else {
                         if (PATH) // trajectory start point (:419-426)
                             h.path[(size_t) L * (size_t) (S + 1) + (size_t) (P.method == 1 ? S : 0)] =
@@ -851,6 +867,26 @@ __device__ __forceinline__ int integrate_ray_gain_slab(const DevProblem &P, unsi
     return any_neg ? 2 : (any_nan ? 3 : 0);
 }
 
+// Overlapped launch (Outputs::pix_done): the CTA waits until the march has closed every ray slot
+// of its pixel.  One thread polls with acquire semantics; the march counted with release
+// semantics after the slot's records and meta word.  (The march's CTAs are all resident or done
+// when this kernel is allowed to start, so the wait cannot starve them.)
+__device__ __forceinline__ void owner_wait_for_pixel(const Outputs &o, unsigned q, unsigned expected)
+{
+    if (o.pix_done == nullptr)
+        return;
+    if (threadIdx.x == 0) {
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(o.pix_done + q) : "memory");
+            if (v >= expected)
+                break;
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+}
+
 #define RTB_OWNER_WARPS 8
 // Resident CTAs per SM the compiler budgets registers for: up to two lane slots (K <= 64) the
 // kernel fits 48 registers with a handful of spills outside the walk, and 40 warps per SM hide
@@ -875,6 +911,7 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, KS <= 2 ? RTB_OWNER_MINB
         s_gv[i] = P.planes[i].gv;
     load_exp_table(exp_tab); // includes __syncthreads()
     const int lane = threadIdx.x & 31, warp = (int) uniform_u32(threadIdx.x >> 5);
+    owner_wait_for_pixel(o, blockIdx.x, (unsigned) P.ab_max);
     const long long p = phys_pixel(P, c, c.pix0 + blockIdx.x);
     const PixelRays pr = pixel_rays(P, p);
     const int S = (P.N - 1) * RTB_N_SUB;
@@ -980,6 +1017,7 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, 3)
         s_gv[i] = P.planes[i].gv;
     load_exp_table(exp_tab); // includes __syncthreads()
     const int lane = threadIdx.x & 31, warp = (int) uniform_u32(threadIdx.x >> 5);
+    owner_wait_for_pixel(o, blockIdx.x, (unsigned) P.ab_max);
     const long long p = phys_pixel(P, c, c.pix0 + blockIdx.x);
     const PixelRays pr = pixel_rays(P, p);
     const int S = (P.N - 1) * RTB_N_SUB;
@@ -1090,8 +1128,30 @@ void launch_unpermute_rows(const DevProblem &P, const double *gathered, int worl
         unpermute_rows_kernel<<<(unsigned) P.sny, 256, 0, st>>>(P, gathered, world, rows_per_dev, image);
 }
 
+template <class Kern>
+static void launch_owner(Kern kern, unsigned blocks, int threads, size_t smem, cudaStream_t st, bool overlap,
+                         const DevProblem &P, const Chunk &c, const Handoff &h, const Outputs &o)
+{
+    if (!overlap) {
+        kern<<<blocks, threads, smem, st>>>(P, c, h, o);
+        return;
+    }
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3((unsigned) threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, P, c, h, o);
+}
+
 void launch_integrate_ase_owner(const DevProblem &P, const Chunk &c, const Handoff &h,
-                                const Outputs &o, cudaStream_t st)
+                                const Outputs &o, cudaStream_t st, bool overlap)
 {
     const long long npix = c.pix1 - c.pix0;
     if (npix <= 0)
@@ -1101,11 +1161,11 @@ void launch_integrate_ase_owner(const DevProblem &P, const Chunk &c, const Hando
     const int ks = (P.K + 31) / 32;
     const size_t smem = sizeof(float *) * (size_t) P.N;
     switch (ks) {
-    case 1: integrate_ase_owner_kernel<1><<<blocks, threads, smem, st>>>(P, c, h, o); break;
-    case 2: integrate_ase_owner_kernel<2><<<blocks, threads, smem, st>>>(P, c, h, o); break;
-    case 3: integrate_ase_owner_kernel<3><<<blocks, threads, smem, st>>>(P, c, h, o); break;
-    case 4: integrate_ase_owner_kernel<4><<<blocks, threads, smem, st>>>(P, c, h, o); break;
-    default: integrate_ase_owner_tiled_kernel<<<blocks, threads, smem, st>>>(P, c, h, o); break; // K > 128
+    case 1: launch_owner(integrate_ase_owner_kernel<1>, blocks, threads, smem, st, overlap, P, c, h, o); break;
+    case 2: launch_owner(integrate_ase_owner_kernel<2>, blocks, threads, smem, st, overlap, P, c, h, o); break;
+    case 3: launch_owner(integrate_ase_owner_kernel<3>, blocks, threads, smem, st, overlap, P, c, h, o); break;
+    case 4: launch_owner(integrate_ase_owner_kernel<4>, blocks, threads, smem, st, overlap, P, c, h, o); break;
+    default: launch_owner(integrate_ase_owner_tiled_kernel, blocks, threads, smem, st, overlap, P, c, h, o); break; // K > 128
     }
 }
 

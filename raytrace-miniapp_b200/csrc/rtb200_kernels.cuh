@@ -22,6 +22,10 @@ struct Handoff {
     unsigned *meta;     // [slots]
     float4 *exit_ray;   // [slots] ray2 = (x, y, a, b) at exit; may be null (ASE binning never reads it)
     float2 *path;       // [slots * ((N-1)*3 + 1)] RAY_DEBUG trajectory (x, y); null except for calc_ray_paths
+    // Grid mode, optional: rays of each logical pixel of the chunk whose hand-off is complete
+    // (counted by the march with release semantics).  Lets the integration of a pixel begin while
+    // the march is still finishing other pixels (programmatic dependent launch); null = not counted.
+    unsigned *pix_done;
 };
 
 // Output selection of the integration kernel.
@@ -36,6 +40,9 @@ struct Outputs {
     // device of a row-cyclic multi-device launch produces: its rows compacted, ready to be
     // gathered; rtb200_unpermute_rows puts the gathered rows where they belong.
     int compact;
+    // Owner kernel only: when not null, the CTA of logical pixel q waits until pix_done[q] has
+    // reached ab_max (see Handoff::pix_done) before it reads the pixel's hand-off.
+    const unsigned *pix_done;
 };
 
 // Persistent flat-state-machine march with refill (work = device counter, reset by the
@@ -45,8 +52,10 @@ void launch_march(const DevProblem &P, const Chunk &c, bool list_mode, const Han
                   int persistent_blocks);
 // ASE (method 1, emission + gain), grid mode: one CTA per source pixel, the pixel's spectrum is
 // owned by the CTA (plain stores), I_ang by atomics.
+// overlap: launch with programmatic stream serialization (the kernel may start as soon as every
+// CTA of the march that precedes it in the stream has signalled or exited; o.pix_done must be set).
 void launch_integrate_ase_owner(const DevProblem &P, const Chunk &c, const Handoff &h,
-                                const Outputs &o, cudaStream_t st);
+                                const Outputs &o, cudaStream_t st, bool overlap = false);
 // Generic: one warp per ray slot, scatter binning with FP64 atomics (list mode, seeded mode,
 // non-identity owner maps) and/or per-ray dumps.
 void launch_integrate_scatter(const DevProblem &P, const Chunk &c, bool list_mode,
