@@ -427,7 +427,11 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
     // Overlapped form (owner kernel, lineshape tables already resident): the march counts the closed
     // ray slots of every pixel, the integration is launched with programmatic stream serialization
     // right behind it - nothing between the two launches - and each of its CTAs waits for its pixel.
-    const bool overlap = ctx->overlap && owner && !ctx->gv_pending;
+#ifdef RTB_HANDOFF_NC // (hand-off read through L1: not safe next to a running march)
+    const bool overlap = false;
+#else
+    const bool overlap = ctx->overlap && owner && !ctx->gv_pending && !ctx->count_steps;
+#endif
     if (overlap)
         RTB_CUDA(ctx->d_pix_done.reserve((size_t) pix_per_chunk));
     for (long long a = pix0; a < pix1; a += pix_per_chunk) {

@@ -230,7 +230,16 @@ __device__ __forceinline__ bool slot_source(const DevProblem &P, const Chunk &c,
 #define RTB_MARCH_THREADS 128
 #define RTB_ST_HUNG 64u  // gave up on the ray (hang guard): reported as invalid
 #define RTB_ST_DEAD 128u // the lane has no ray and there is none left to claim
-template <bool LIST, bool PATH, bool COUNT>
+// Overlapped integration (Handoff::pix_done): one more closed ray slot of a pixel.  The slot's
+// records and meta word were stored by THIS thread, so a release reduction orders them before the
+// count; no fence of wider scope (__threadfence() would also invalidate the SM's L1 - CCTL.IVALL -
+// and with it the march's tables, once per ray).
+__device__ __forceinline__ void count_closed_slot(unsigned *counter)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+
+template <bool LIST, bool PATH, bool COUNT, bool OVL = false>
 __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
     march_flat_kernel(const DevProblem P, const Chunk c, const Handoff h, FailState *fail,
                       unsigned long long *work)
@@ -287,10 +296,8 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
             h.exit_ray[L] = e;
         }
         h.meta[L] = meta;
-        if (!LIST && h.pix_done) { // this ray's records and meta word first, then the count
-            __threadfence();
-            atomicAdd(&h.pix_done[L / (unsigned) P.ab_max], 1u);
-        }
+        if (OVL) // this ray's records and meta word first, then the count
+            count_closed_slot(h.pix_done + L / (unsigned) P.ab_max);
         if (COUNT)
             total_steps += m.steps;
         pending = false;
@@ -317,7 +324,7 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
                 if (run_next >= n_slots)
                     exhausted = true;
             }
-            if (exhausted && !signalled) {
+            if (OVL && exhausted && !signalled) {
                 // the work queue is empty: the integration kernel may start filling the SMs that
                 // the march's last CTAs leave (it waits per pixel on Handoff::pix_done)
                 asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -337,10 +344,8 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
                     const bool active = slot_source<LIST>(P, c, L, rx, ry, ra, rb, ta, tb);
                     if (!active) {
                         h.meta[L] = RTB_META_INACTIVE;
-                        if (!LIST && h.pix_done) {
-                            __threadfence();
-                            atomicAdd(&h.pix_done[L / (unsigned) P.ab_max], 1u);
-                        }
+                        if (OVL)
+                            count_closed_slot(h.pix_done + L / (unsigned) P.ab_max);
                     } else {
                         if (PATH) // trajectory start point (:419-426)
                             h.path[(size_t) L * (size_t) (S + 1) + (size_t) (P.method == 1 ? S : 0)] =
@@ -387,12 +392,12 @@ __global__ void __launch_bounds__(RTB_MARCH_THREADS, RTB_MARCH_MINBLOCKS)
     }
 }
 
-template <bool LIST, bool PATH, bool COUNT>
+template <bool LIST, bool PATH, bool COUNT, bool OVL = false>
 static void launch_march_t(const DevProblem &P, const Chunk &c, const Handoff &h, FailState *fail,
                            cudaStream_t st, unsigned long long *work, int persistent_blocks, long long n)
 {
     const size_t smem = sizeof(PlaneLite) * (size_t) P.N;
-    auto kern = march_flat_kernel<LIST, PATH, COUNT>;
+    auto kern = march_flat_kernel<LIST, PATH, COUNT, OVL>;
     if (smem > 40 * 1024) // deep stacks of planes (hundreds): opt in to the large carve-out
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     long long blocks = persistent_blocks;
@@ -423,6 +428,8 @@ void launch_march(const DevProblem &P, const Chunk &c, bool list_mode, const Han
         launch_march_t<true, false, false>(P, c, h, fail, st, work, persistent_blocks, n);
     else if (count_steps)
         launch_march_t<false, false, true>(P, c, h, fail, st, work, persistent_blocks, n);
+    else if (h.pix_done) // overlapped integration: closed slots counted per pixel, early trigger
+        launch_march_t<false, false, false, true>(P, c, h, fail, st, work, persistent_blocks, n);
     else
         launch_march_t<false, false, false>(P, c, h, fail, st, work, persistent_blocks, n);
 }
@@ -459,6 +466,34 @@ __device__ __forceinline__ float rcp_approx(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+
+// The exp branch of the update with the reciprocal seeded by the double-precision approximation
+// (MUFU.RCP64H: input and result carry 20 significand bits, relative error < 2^-19) and one
+// second-order step, 1/gl to ~2^-57: one XU instruction per update less than the single-precision
+// seed + widening (the XU pipe issues a warp instruction every 8 cycles and the update spends
+// three more of them on widenings), one DFMA more.
+__device__ __forceinline__ double rcp64h_approx(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+template <class KC>
+__device__ __forceinline__ double ase_update_large_r64(double Iv, double gl, double el, const KC &C)
+{
+    const double e = exp_core(gl, C);
+    const double r0 = rcp64h_approx(gl);
+    const double d = __fma_rn(-gl, r0, 1.0);
+    const double d2 = __fma_rn(d, d, d);
+    const double u0 = el * r0;
+    const double u = __fma_rn(u0, d2, u0); // el / gl
+    return __fma_rn(u, e, __fma_rn(Iv, e, -u));
+}
+#ifdef RTB_RCP64H
+#define RTB_UPDATE_LARGE(Iv, gl, el, glf, KC) ase_update_large_r64(Iv, gl, el, KC)
+#else
+#define RTB_UPDATE_LARGE(Iv, gl, el, glf, KC) ase_update_large(Iv, gl, el, rcp_approx(glf), KC)
+#endif
 
 // A value every lane of the warp holds, re-issued through a warp reduction: the result lives in
 // a uniform register, so the compiler KNOWS that branches and loop bounds derived from it are
@@ -612,6 +647,16 @@ struct PinnedConsts {
     }
 };
 
+// Loads of the hand-off (records, meta words) in the owner kernels.  The data is read exactly once,
+// so it need not be kept in L1 next to the lineshape rows; and when the kernel overlaps the march
+// (Outputs::pix_done) it MUST not be: a line that straddles two pixels could have been brought into
+// the SM's L1 by the first pixel's CTA before the march had written the second pixel's part.
+#ifdef RTB_HANDOFF_NC
+#define RTB_HANDOFF_LD(p) __ldg(p)
+#else
+#define RTB_HANDOFF_LD(p) __ldcg(p)
+#endif
+
 template <int KS>
 __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const float *const *s_gv,
                                                       const SegRec *seg, unsigned meta, int lane,
@@ -638,7 +683,7 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
         unsigned gvl_abs = 0u;
         bool nonzero = false;
         if (lane < cnt) {
-            const int4 rv = __ldg(reinterpret_cast<const int4 *>(&seg[c0 + lane]));
+            const int4 rv = RTB_HANDOFF_LD(reinterpret_cast<const int4 *>(&seg[c0 + lane]));
             const float *row = s_gv[(c0 + lane) / RTB_N_SUB + 1] + (size_t) rv.z * K;
             const unsigned long long ra = reinterpret_cast<unsigned long long>(row);
             gvl_abs = (unsigned) rv.x & 0x7fffffffu;
@@ -648,6 +693,18 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
                          "r"((unsigned) rv.x), "r"((unsigned) rv.y), "r"((unsigned) ra),
                          "r"((unsigned) (ra >> 32))
                          : "memory");
+#ifdef RTB_OWNER_PREFETCH_ROWS
+            // the lineshape rows of ALL the records of this batch are requested into L1 now, by the
+            // lanes that resolved their addresses: the walk then finds them there (it asks for a
+            // row only one record ahead, which covers an L1 hit but not an L2 round trip)
+            if (nonzero) {
+                const char *rb = reinterpret_cast<const char *>(row);
+                const int bytes = 4 * K;
+                for (int off = 0; off < bytes; off += 128)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(rb + off));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(rb + bytes - 4));
+            }
+#endif
         }
         __syncwarp();
         // The records that change anything, as a warp-uniform bit mask: the walk below visits
@@ -693,18 +750,35 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
                     Iv[q] = ase_update_library(Iv[q], (double) glf[q], (double) elf[q]);
                 return;
             }
+#ifdef RTB_JOINT_EXP
+            // Every lane of every slot on the exp branch (the common record): ONE vote for the
+            // record, and the slots' updates in one basic block, so that the independent FP64
+            // chains of the slots interleave.
+            if (KS > 1) {
+                bool any_small = false;
+#pragma unroll
+                for (int q = 0; q < KS; q++)
+                    any_small = any_small || small[q];
+                if (__builtin_expect(!__any_sync(0xffffffffu, any_small), 1)) {
+#pragma unroll
+                    for (int q = 0; q < KS; q++)
+                        Iv[q] = RTB_UPDATE_LARGE(Iv[q], (double) glf[q], (double) elf[q], glf[q], KC);
+                    return;
+                }
+            }
+#endif
 #pragma unroll
             for (int q = 0; q < KS; q++) {
                 const double gl = (double) glf[q], el = (double) elf[q];
                 // three straight-line variants: the common one (every lane of the slot on the
                 // exp branch) carries no select and no dead Taylor result
                 if (__builtin_expect(!__any_sync(0xffffffffu, small[q]), 1)) {
-                    Iv[q] = ase_update_large(Iv[q], gl, el, rcp_approx(glf[q]), KC);
+                    Iv[q] = RTB_UPDATE_LARGE(Iv[q], gl, el, glf[q], KC);
                 } else if (__builtin_expect(__all_sync(0xffffffffu, small[q]), 0)) {
                     Iv[q] = ase_update_small(Iv[q], gl, el, KC);
                 } else {
                     const double a = ase_update_small(Iv[q], gl, el, KC);
-                    const double b = ase_update_large(Iv[q], gl, el, rcp_approx(glf[q]), KC);
+                    const double b = RTB_UPDATE_LARGE(Iv[q], gl, el, glf[q], KC);
                     Iv[q] = small[q] ? a : b;
                 }
             }
@@ -877,12 +951,13 @@ __device__ __forceinline__ void owner_wait_for_pixel(const Outputs &o, unsigned 
         return;
     if (threadIdx.x == 0) {
         unsigned v;
-        for (;;) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(o.pix_done + q) : "memory");
+        for (;;) { // relaxed polling (an acquire load would invalidate the SM's L1 at every poll)
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(o.pix_done + q) : "memory");
             if (v >= expected)
                 break;
             __nanosleep(200);
         }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory"); // once per CTA
     }
     __syncthreads();
 }
@@ -940,7 +1015,7 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, KS <= 2 ? RTB_OWNER_MINB
         {
             const int t = t0 + lane * RTB_OWNER_WARPS;
             if (t < pr.cnt) {
-                meta_l = __ldg(&h.meta[slot0 + t]);
+                meta_l = RTB_HANDOFF_LD(&h.meta[slot0 + t]);
                 const int ab = pr.ab0 + t * (int) P.n_parallel;
                 const int ka = ab / P.snb, m = ab - ka * P.snb;
                 const int ba = __ldg(&P.binA[ka]), bb = __ldg(&P.binB[m]);
@@ -1045,7 +1120,7 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, 3)
             {
                 const int t = t0 + lane * RTB_OWNER_WARPS;
                 if (t < pr.cnt) {
-                    meta_l = __ldg(&h.meta[slot0 + t]);
+                    meta_l = RTB_HANDOFF_LD(&h.meta[slot0 + t]);
                     const int ab = pr.ab0 + t * (int) P.n_parallel;
                     const int ka = ab / P.snb, m = ab - ka * P.snb;
                     const int ba = __ldg(&P.binA[ka]), bb = __ldg(&P.binB[m]);
