@@ -96,7 +96,9 @@ typedef struct rtb200_problem {
 /* Per-call device timings (CUDA events on the context's stream), milliseconds. */
 typedef struct rtb200_timings {
     float h2d_ms;       /* staging upload */
-    float march_ms;     /* refractive march kernel(s) */
+    float march_ms;     /* refractive march kernel(s); ASE grid launches overlap the march's tail with the
+                           integration (programmatic dependent launch): there this is the time of BOTH
+                           kernels and integrate_ms is 0 - RTB200_OVERLAP=0 runs them one after the other */
     float integrate_ms; /* frequency integration + binning kernel(s) */
     float d2h_ms;       /* image / I_ang download */
     float total_ms;     /* first event to last event */

@@ -101,8 +101,14 @@ struct rtb200_ctx {
     DevBuf<char> d_blob, d_gv; // d_gv: the lineshape tables (read by the integration only)
     DevBuf<char> d_cells;      // per-cell records, derived on the device (CellBlob, rtb200_pack.h)
     DevBuf<char> d_gvd;        // lineshape tables in double (gain-only problems), widened on the device
-    DevBuf<unsigned> d_pix_done; // per-pixel completion counts of the march (overlapped integration)
-    bool overlap = false;        // RTB200_OVERLAP=1: start the integration while the march drains
+    // Overlapped march + integration (owner kernel; RTB200_OVERLAP=0 turns it off): the march counts
+    // the closed ray slots of every pixel, the integration is launched with programmatic stream
+    // serialization right behind it and each of its CTAs waits for its own pixel.
+    DevBuf<unsigned> d_pix_done; // per-pixel completion counts
+    DevBuf<unsigned> d_gv_flag;  // epoch of the lineshape tables resident in d_gv (written by a copy)
+    unsigned *h_gv_epoch = nullptr; // pinned source of that copy
+    unsigned gv_epoch = 0;
+    bool overlap = true;
     const rtb200_problem *gv_pending = nullptr; // tables not filled/uploaded yet (create_image)
     size_t gv_bytes = 0;
     DevProblem prob;
@@ -290,7 +296,9 @@ bool injective(const int *t, int n, int range)
 }
 
 // Fills and uploads the lineshape tables if that is still pending (see stage_impl).
-int flush_gv(rtb200_ctx *ctx, cudaStream_t st)
+// device_flag: `st` does NOT wait for the copy; instead the epoch word d_gv_flag is written behind
+// it on the copy stream and the integration kernel polls that word (overlapped launch).
+int flush_gv(rtb200_ctx *ctx, cudaStream_t st, bool device_flag = false)
 {
     if (!ctx->gv_pending)
         return RTB200_OK;
@@ -304,6 +312,12 @@ int flush_gv(rtb200_ctx *ctx, cudaStream_t st)
     if (!ctx->prob.use_emis) { // (the plane descriptors were uploaded on ctx->stream: stage_done)
         RTB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_done, 0));
         launch_widen_gv(ctx->prob.planes, ctx->prob.N, ctx->prob.K, ctx->copy_stream);
+    }
+    if (device_flag) {
+        *ctx->h_gv_epoch = ++ctx->gv_epoch;
+        RTB_CUDA(cudaMemcpyAsync(ctx->d_gv_flag.p, ctx->h_gv_epoch, sizeof(unsigned), cudaMemcpyHostToDevice,
+                                 ctx->copy_stream));
+        return RTB200_OK;
     }
     RTB_CUDA(cudaEventRecord(ctx->gv_ready, ctx->copy_stream));
     RTB_CUDA(cudaStreamWaitEvent(st, ctx->gv_ready, 0));
@@ -424,16 +438,18 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
         return rc;
     Handoff h{ ctx->d_seg.p, ctx->d_meta.p, need_exit ? ctx->d_exit.p : nullptr, nullptr, nullptr };
     const bool owner = ctx->owner_ok && !out.Iv && !out.error;
-    // Overlapped form (owner kernel, lineshape tables already resident): the march counts the closed
-    // ray slots of every pixel, the integration is launched with programmatic stream serialization
-    // right behind it - nothing between the two launches - and each of its CTAs waits for its pixel.
+    // Overlapped form (owner kernel): the march counts the closed ray slots of every pixel, the
+    // integration is launched with programmatic stream serialization right behind it - nothing
+    // between the two launches in the stream - and each of its CTAs waits for its pixel (and, when
+    // the lineshape tables are still on their way, for the word that follows them).
 #ifdef RTB_HANDOFF_NC // (hand-off read through L1: not safe next to a running march)
     const bool overlap = false;
 #else
-    const bool overlap = ctx->overlap && owner && !ctx->gv_pending && !ctx->count_steps;
+    const bool overlap = ctx->overlap && owner && !ctx->count_steps;
 #endif
     if (overlap)
         RTB_CUDA(ctx->d_pix_done.reserve((size_t) pix_per_chunk));
+    bool wait_gv = false; // this launch's integration kernels poll the tables' epoch word
     for (long long a = pix0; a < pix1; a += pix_per_chunk) {
         Chunk c;
         std::memset(&c, 0, sizeof(c));
@@ -449,6 +465,16 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
             oo.pix_done = ctx->d_pix_done.p;
             const size_t e0 = new_event(ctx, st);
             launch_march(P, c, false, ho, ctx->d_fail, ctx->count_steps, st, ctx->d_work, ctx->march_blocks);
+            if (ctx->gv_pending) { // host packs the lineshape tables while the march runs
+                rc = flush_gv(ctx, st, true);
+                if (rc)
+                    return rc;
+                wait_gv = true;
+            }
+            if (wait_gv) {
+                oo.gv_flag = ctx->d_gv_flag.p;
+                oo.gv_epoch = ctx->gv_epoch;
+            }
             launch_integrate_ase_owner(P, c, ho, oo, st, true);
             const size_t e2 = new_event(ctx, st);
             ctx->ev_march.push_back({ e0, e2 }); // (the two kernels overlap: one interval)
@@ -567,7 +593,12 @@ int rtb200_create(int device, rtb200_ctx **out)
         ctx->march_blocks = std::max(1, atoi(s));
     if (const char *s = getenv("RTB200_HANDOFF_MB"))
         ctx->handoff_bytes = (size_t) std::max(1, atoi(s)) << 20;
-    if (const char *s = getenv("RTB200_OVERLAP")) // start the integration while the march drains
+    if ((e = cudaMallocHost((void **) &ctx->h_gv_epoch, sizeof(unsigned))) != cudaSuccess)
+        return fail(e);
+    *ctx->h_gv_epoch = 0;
+    if ((e = ctx->d_gv_flag.reserve(1)) != cudaSuccess || (e = cudaMemset(ctx->d_gv_flag.p, 0, sizeof(unsigned))) != cudaSuccess)
+        return fail(e);
+    if (const char *s = getenv("RTB200_OVERLAP")) // 0: march and integration strictly one after the other
         ctx->overlap = atoi(s) != 0;
     if (const char *s = getenv("RTB200_COUNT_STEPS"))
         ctx->count_steps = atoi(s) != 0;
@@ -591,6 +622,10 @@ void rtb200_destroy(rtb200_ctx *ctx)
     ctx->d_cells.release();
     ctx->d_gvd.release();
     ctx->d_pix_done.release();
+    ctx->d_gv_flag.release();
+    if (ctx->h_gv_epoch)
+        cudaFreeHost(ctx->h_gv_epoch);
+    ctx->h_gv_epoch = nullptr;
     ctx->d_seg.release();
     ctx->d_meta.release();
     ctx->d_exit.release();

@@ -957,7 +957,17 @@ __device__ __forceinline__ void owner_wait_for_pixel(const Outputs &o, unsigned 
                 break;
             __nanosleep(200);
         }
-        asm volatile("fence.acq_rel.gpu;" ::: "memory"); // once per CTA
+        if (o.gv_flag != nullptr) { // ... and until the lineshape tables of this image have arrived
+            for (;;) {
+                asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(o.gv_flag) : "memory");
+                if (v == o.gv_epoch)
+                    break;
+                __nanosleep(500);
+            }
+            asm volatile("fence.acq_rel.sys;" ::: "memory"); // (the writer is a copy engine)
+        } else {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory"); // once per CTA
+        }
     }
     __syncthreads();
 }

@@ -43,6 +43,11 @@ struct Outputs {
     // Owner kernel only: when not null, the CTA of logical pixel q waits until pix_done[q] has
     // reached ab_max (see Handoff::pix_done) before it reads the pixel's hand-off.
     const unsigned *pix_done;
+    // Overlapped launch while the lineshape tables are still being uploaded on the copy stream
+    // (rtb200_create_image): when not null, the CTA also waits until *gv_flag == gv_epoch - the word
+    // is written by a 4-byte copy that follows the tables' copy on the same stream.
+    const unsigned *gv_flag;
+    unsigned gv_epoch;
 };
 
 // Persistent flat-state-machine march with refill (work = device counter, reset by the

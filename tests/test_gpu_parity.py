@@ -347,3 +347,33 @@ def test_create_image_from_dat_bytes(name, request, ctx):
     assert rel_l2(ang, ref_ang) < 1e-13
     with pytest.raises(Exception):
         ctx.create_image_from_dat(payload[1:200], 8, 8)
+
+
+def test_overlapped_launch_matches_serial(ase_small, monkeypatch):
+    """The default ASE launch starts the integration while the march drains (programmatic dependent
+    launch, per-pixel completion counts; with rtb200_create_image's lazily uploaded lineshape
+    tables also the epoch word behind their copy).  Same image bits as RTB200_OVERLAP=0, image
+    after image on one context, also when the hand-off is cut into pixel-range chunks."""
+    from raytrace_miniapp_b200 import lib as rl
+    p, _ = ase_small
+    monkeypatch.setenv("RTB200_OVERLAP", "0")
+    c0 = rl.Context(0)
+    img0, ang0 = c0.create_image(p)
+    t0 = c0.timings()
+    assert t0["march_ms"] > 0 and t0["integrate_ms"] > 0
+    c0.close()
+    monkeypatch.setenv("RTB200_OVERLAP", "1")
+    c1 = rl.Context(0)
+    for _ in range(3):
+        img1, ang1 = c1.create_image(p)
+        assert np.array_equal(img0, img1)
+        assert rel_l2(ang1, ang0) < 1e-13  # (atomics: order of the additions)
+        t1 = c1.timings()
+        assert t1["march_ms"] > 0 and t1["integrate_ms"] == 0 and t1["kernel_launches"] == 2
+    c1.close()
+    monkeypatch.setenv("RTB200_HANDOFF_MB", "16")  # several chunks, each march + integration overlapped
+    c2 = rl.Context(0)
+    img2, ang2 = c2.create_image(p)
+    assert c2.timings()["kernel_launches"] > 2
+    assert np.array_equal(img0, img2) and rel_l2(ang2, ang0) < 1e-13
+    c2.close()

@@ -29,7 +29,7 @@ def child(name):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ctx = lib.Context(0)
     for cname, p in cases:
-        e = p.euv
+        e = p.euv_beam
         n_pix = ctx.stage(p)
         img = torch.zeros(e.nx * e.ny * e.nv, dtype=torch.float64, device=dev)
         ang = torch.zeros(e.na * e.nb, dtype=torch.float64, device=dev)
