@@ -467,34 +467,6 @@ __device__ __forceinline__ float rcp_approx(float x)
     return r;
 }
 
-// The exp branch of the update with the reciprocal seeded by the double-precision approximation
-// (MUFU.RCP64H: input and result carry 20 significand bits, relative error < 2^-19) and one
-// second-order step, 1/gl to ~2^-57: one XU instruction per update less than the single-precision
-// seed + widening (the XU pipe issues a warp instruction every 8 cycles and the update spends
-// three more of them on widenings), one DFMA more.
-__device__ __forceinline__ double rcp64h_approx(double x)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    return r;
-}
-template <class KC>
-__device__ __forceinline__ double ase_update_large_r64(double Iv, double gl, double el, const KC &C)
-{
-    const double e = exp_core(gl, C);
-    const double r0 = rcp64h_approx(gl);
-    const double d = __fma_rn(-gl, r0, 1.0);
-    const double d2 = __fma_rn(d, d, d);
-    const double u0 = el * r0;
-    const double u = __fma_rn(u0, d2, u0); // el / gl
-    return __fma_rn(u, e, __fma_rn(Iv, e, -u));
-}
-#ifdef RTB_RCP64H
-#define RTB_UPDATE_LARGE(Iv, gl, el, glf, KC) ase_update_large_r64(Iv, gl, el, KC)
-#else
-#define RTB_UPDATE_LARGE(Iv, gl, el, glf, KC) ase_update_large(Iv, gl, el, rcp_approx(glf), KC)
-#endif
-
 // A value every lane of the warp holds, re-issued through a warp reduction: the result lives in
 // a uniform register, so the compiler KNOWS that branches and loop bounds derived from it are
 // warp-uniform (no divergence check in front of the votes, no reconvergence points).
@@ -693,18 +665,6 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
                          "r"((unsigned) rv.x), "r"((unsigned) rv.y), "r"((unsigned) ra),
                          "r"((unsigned) (ra >> 32))
                          : "memory");
-#ifdef RTB_OWNER_PREFETCH_ROWS
-            // the lineshape rows of ALL the records of this batch are requested into L1 now, by the
-            // lanes that resolved their addresses: the walk then finds them there (it asks for a
-            // row only one record ahead, which covers an L1 hit but not an L2 round trip)
-            if (nonzero) {
-                const char *rb = reinterpret_cast<const char *>(row);
-                const int bytes = 4 * K;
-                for (int off = 0; off < bytes; off += 128)
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(rb + off));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(rb + bytes - 4));
-            }
-#endif
         }
         __syncwarp();
         // The records that change anything, as a warp-uniform bit mask: the walk below visits
@@ -750,35 +710,18 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
                     Iv[q] = ase_update_library(Iv[q], (double) glf[q], (double) elf[q]);
                 return;
             }
-#ifdef RTB_JOINT_EXP
-            // Every lane of every slot on the exp branch (the common record): ONE vote for the
-            // record, and the slots' updates in one basic block, so that the independent FP64
-            // chains of the slots interleave.
-            if (KS > 1) {
-                bool any_small = false;
-#pragma unroll
-                for (int q = 0; q < KS; q++)
-                    any_small = any_small || small[q];
-                if (__builtin_expect(!__any_sync(0xffffffffu, any_small), 1)) {
-#pragma unroll
-                    for (int q = 0; q < KS; q++)
-                        Iv[q] = RTB_UPDATE_LARGE(Iv[q], (double) glf[q], (double) elf[q], glf[q], KC);
-                    return;
-                }
-            }
-#endif
 #pragma unroll
             for (int q = 0; q < KS; q++) {
                 const double gl = (double) glf[q], el = (double) elf[q];
                 // three straight-line variants: the common one (every lane of the slot on the
                 // exp branch) carries no select and no dead Taylor result
                 if (__builtin_expect(!__any_sync(0xffffffffu, small[q]), 1)) {
-                    Iv[q] = RTB_UPDATE_LARGE(Iv[q], gl, el, glf[q], KC);
+                    Iv[q] = ase_update_large(Iv[q], gl, el, rcp_approx(glf[q]), KC);
                 } else if (__builtin_expect(__all_sync(0xffffffffu, small[q]), 0)) {
                     Iv[q] = ase_update_small(Iv[q], gl, el, KC);
                 } else {
                     const double a = ase_update_small(Iv[q], gl, el, KC);
-                    const double b = RTB_UPDATE_LARGE(Iv[q], gl, el, glf[q], KC);
+                    const double b = ase_update_large(Iv[q], gl, el, rcp_approx(glf[q]), KC);
                     Iv[q] = small[q] ? a : b;
                 }
             }

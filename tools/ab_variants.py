@@ -2,7 +2,7 @@
 """A/B of library builds on the GPU box, device-resident inputs (the bench's `value` path):
 
     python tools/ab_variants.py [name ...]        name = "tree" or a file stem under .variants/
-                                                  name+ovl = the same build with RTB200_OVERLAP=1
+                                                  name@KEY=VAL,KEY=VAL = the same build with that environment
 
 Each build runs in a process of its own (RTB200_LIB): ASE_medium-synth and ASE_small staged once,
 then 3 warm-up + 9 timed launches each (CUDA events on the launching stream, L2 flushed between
@@ -78,10 +78,11 @@ def main():
     for name in names:
         env = dict(os.environ)
         base = name
-        env.pop("RTB200_OVERLAP", None)
-        if name.endswith("+ovl"):
-            base = name[:-4]
-            env["RTB200_OVERLAP"] = "1"
+        if "@" in base:  # name@KEY=VAL,KEY=VAL: environment of that run
+            base, kv = base.split("@", 1)
+            for item in kv.split(","):
+                k, v = item.split("=", 1)
+                env[k] = v
         if base != "tree":
             env["RTB200_LIB"] = os.path.join(ROOT, ".variants", base + ".so")
         else:
