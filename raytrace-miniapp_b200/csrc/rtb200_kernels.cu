@@ -8,9 +8,16 @@
 //                              bins: ASE gain + emission integration (FP64), per-pixel spectrum
 //                              accumulated in registers (no atomics), I_ang by warp-shuffle
 //                              reduction + one FP64 atomic per ray.
-//   integrate_scatter_kernel   one warp per ray, lanes = frequency bins: seeded (gain-only) and
-//                              list-mode rays, binning by the exit ray with FP64 atomics;
-//                              also the per-ray dump used by rtb200_calc_rays.
+//   integrate_seeded_kernel    the seeded image of create_image (grid mode, gain-only): one warp
+//                              per 64 ray slots, lanes = frequency bins, per-ray scalars by one lane
+//                              per ray, binning by the exit ray with run-length combined atomics.
+//   integrate_scatter_kernel   one warp per ray, lanes = frequency bins: list-mode rays, emission
+//                              along listed rays, K > 128 seeded; binning by the exit ray with FP64
+//                              atomics; also the per-ray dump used by rtb200_calc_rays.
+//
+// ASE grid launches overlap the two kernels: the march counts the closed ray slots of every pixel
+// (Handoff::pix_done) and releases its dependents when its work queue is empty; the owner kernel
+// is launched with programmatic stream serialization and each of its CTAs waits for its pixel.
 //
 // There are no tensor-core instructions here on purpose: the path is not a dense contraction
 // (SURVEY.md §8d); the binding unit is the FP64 pipe.
