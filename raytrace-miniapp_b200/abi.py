@@ -185,6 +185,12 @@ class Problem:
                      C.pointer(sd) if sd is not None else None)
         return p, (eb, sb, planes, sd, self)
 
+    def marshal(self):
+        """The C structure built ONCE (what an application that holds a create_image_struct passes
+        to every call): a view of this problem whose c_struct() costs nothing.  The arrays and the
+        N_start / N_parallel of the moment are captured; marshal again after changing them."""
+        return Marshalled(self)
+
     def rays(self):
         """The ray list create_image builds (src/RayTraceImage.cpp:300-328), as a structured array."""
         g = self.ray_grid
@@ -197,3 +203,17 @@ class Problem:
         r = np.empty(ijkm.size, ray_dtype)
         r["x"], r["y"], r["a"], r["b"] = c.x[i], c.y[j], c.a[k], c.b[m]
         return r
+
+
+class Marshalled:
+    """Problem + its rtb200_problem structure (Problem.marshal); accepted wherever a Problem is."""
+
+    def __init__(self, problem):
+        self.problem = problem
+        self._c = problem.c_struct()
+
+    def c_struct(self):
+        return self._c
+
+    def __getattr__(self, name):
+        return getattr(self.problem, name)

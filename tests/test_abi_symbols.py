@@ -41,3 +41,17 @@ def test_fails_loudly_without_a_device(rtlib):
     with pytest.raises(rtlib.RTB200Error) as e:
         rtlib.Context(0)
     assert e.value.code == abi.ERR_CUDA
+
+
+def test_marshalled_problem_is_a_view_of_the_problem(ase_small):
+    """Problem.marshal(): the rtb200_problem structure built once (what bench.py's end-to-end leg
+    passes to every call); same pointers and scalars as a fresh c_struct(), attributes pass through."""
+    p, _ = ase_small
+    m = p.marshal()
+    c0, _keep0 = p.c_struct()
+    c1, _keep1 = m.c_struct()
+    assert m.c_struct()[0] is c1  # built once
+    assert (c1.N, c1.N_start, c1.N_parallel) == (c0.N, c0.N_start, c0.N_parallel) == (p.N, p.N_start, p.N_parallel)
+    assert m.euv_beam is p.euv_beam and m.n_rays == p.n_rays and m.method == p.method
+    for i in range(p.N):
+        assert c1.gain[i].Nx == p.gain[i].Nx and c1.gain[i].Nv == p.euv_beam.nv
