@@ -38,15 +38,37 @@ FP64_INSTR_PER_UPDATE = 32  # SURVEY.md §8d convention (ASE mode)
 TMP = os.path.join(ROOT, ".bench_tmp")
 
 
+WORKLOAD = "ase_medium"  # --workload: which BASELINE.json configuration the step traces
+
+
 def workload(n_gpus, scaling):
+    """The headline workload (BASELINE.json configs[1], and configs[2] when sharded), or with
+    --workload the synthetic families of configs[3] / configs[4]: s4 / s4b / s4x = gain planes 2 /
+    4 / 8 times finer per axis with 4x the image resolution, spectral<K> = K frequency bins with 4x
+    the angles.  Weak scaling multiplies the image rows (the sharded axis) by the GPU count."""
     small, _ = problem_io.load_npz(os.path.join(ROOT, "tests", "golden", "ase_small.npz"))
     rows = n_gpus if scaling == "weak" else 1
-    p = synth.ase_medium_synth(small, rows_factor=rows)
+    tail = ", ny x%d for weak scaling" % rows if rows > 1 else ""
+    if WORKLOAD == "ase_medium":
+        p = synth.ase_medium_synth(small, rows_factor=rows)
+        e = p.euv_beam
+        return p, ("ASE_medium-synth (ASE_small refined as -scale=8: %dx%dx%dx%d rays, N=%d planes, "
+                   "nv=%d%s)" % (e.nx, e.ny, e.na, e.nb, p.N, e.nv, tail))
+    if WORKLOAD in ("s4", "s4b", "s4x"):
+        f = {"s4": 2, "s4b": 4, "s4x": 8}[WORKLOAD]
+        p = synth.s4(small, f, 2)
+        label = "S4 family: ASE_small with gain planes %dx finer per axis (%dx%d nodes), image 2x per axis" % (
+            f, p.gain[1].Nx, p.gain[1].Ny)
+    elif WORKLOAD.startswith("spectral"):
+        K = int(WORKLOAD[len("spectral"):] or 512)
+        p = synth.spectral(small, K, angle_factor=2)
+        label = "spectral sweep: ASE_small with %d frequency bins, angles 2x per axis" % K
+    else:
+        raise SystemExit("unknown --workload %r" % WORKLOAD)
+    if rows > 1:
+        p.euv_beam = synth.refine_rows(p.euv_beam, rows)
     e = p.euv_beam
-    name = ("ASE_medium-synth (ASE_small refined as -scale=8: %dx%dx%dx%d rays, N=%d planes, "
-            "nv=%d%s)" % (e.nx, e.ny, e.na, e.nb, p.N, e.nv,
-                          ", ny x%d for weak scaling" % rows if rows > 1 else ""))
-    return p, name
+    return p, "%s: %dx%dx%dx%d rays, N=%d planes, nv=%d%s" % (label, e.nx, e.ny, e.na, e.nb, p.N, e.nv, tail)
 
 
 class ClockSampler:
@@ -394,7 +416,7 @@ def run_gpu(args):
                                          if st["integrate_ms"] == 0.0 else
                                          {"march": st["march_ms"], "integrate": st["integrate_ms"]}),
                   "steps": ks, "parallelism": sj.exchange_name()}
-        parity = {"checked": "sharded image / I_ang of the fixed ASE_medium-synth at %d GPUs against the "
+        parity = {"checked": "sharded image / I_ang of the fixed image (strong.workload) at %d GPUs against the "
                              "single-GPU result computed in this run on rank 0" % world,
                   "image_bit_identical_to_single_gpu": same_bits, "I_ang_relL2": ang_err}
 
@@ -532,9 +554,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="rtb200", choices=["rtb200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--workload", default="ase_medium",
+                    help="ase_medium (default, the headline), s4 | s4b | s4x (config 4), spectral<K> (config 5)")
     ap.add_argument("--cpu-stride", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     if args.impl == "reference":
         run_reference(args)
     else:
