@@ -640,8 +640,10 @@ template <int KS>
 __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const float *const *s_gv,
                                                       const SegRec *seg, unsigned meta, int lane,
                                                       const int (&koff)[KS], double (&Iv)[KS],
-                                                      const PinnedConsts &KC, unsigned slab)
+                                                      const PinnedConsts &KC, unsigned slab,
+                                                      unsigned sgv_shared = 0u)
 {
+    (void) sgv_shared;
     // slab: shared-space address of this warp's 32 x 16-byte record slab (opaque register)
     const int lo = meta & 0xfff, hi = (meta >> 12) & 0xfff;
     const int K = P.K;
@@ -663,7 +665,17 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
         bool nonzero = false;
         if (lane < cnt) {
             const int4 rv = RTB_HANDOFF_LD(reinterpret_cast<const int4 *>(&seg[c0 + lane]));
+#ifdef RTB_OWNER_SEG_BASE
+            // (the table of lineshape base pointers through its shared-space address, kept opaque in
+            // a uniform register: otherwise it is rebuilt from the CTA's shared window at every use)
+            unsigned long long gvp;
+            asm volatile("ld.shared.u64 %0, [%1];"
+                         : "=l"(gvp)
+                         : "r"(sgv_shared + 8u * (unsigned) ((c0 + lane) / RTB_N_SUB + 1)));
+            const float *row = reinterpret_cast<const float *>(gvp) + (size_t) rv.z * K;
+#else
             const float *row = s_gv[(c0 + lane) / RTB_N_SUB + 1] + (size_t) rv.z * K;
+#endif
             const unsigned long long ra = reinterpret_cast<unsigned long long>(row);
             gvl_abs = (unsigned) rv.x & 0x7fffffffu;
             // gvl == 0 && evl == 0 (either sign of zero): gl = el = 0, the update is the identity
@@ -967,6 +979,16 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, KS <= 2 ? RTB_OWNER_MINB
     }
     const PinnedConsts KC(P.kfp_g, exp_tab);
     const unsigned slab_addr = uniform_u32((unsigned) __cvta_generic_to_shared(&rec_slab[warp][0]));
+#ifdef RTB_OWNER_SEG_BASE
+    // The pixel's first hand-off record as a pair of uniform values: a ray's records are then one
+    // 32-bit multiply-add away (left alone, the 64-bit product slot * S is rebuilt for every ray).
+    const unsigned long long seg_pix = reinterpret_cast<unsigned long long>(h.seg + slot0 * S);
+    const unsigned seg_lo = uniform_u32((unsigned) seg_pix), seg_hi = uniform_u32((unsigned) (seg_pix >> 32));
+    const unsigned ray_bytes = (unsigned) S * (unsigned) sizeof(SegRec);
+    const unsigned sgv_shared = uniform_u32((unsigned) __cvta_generic_to_shared(s_gv));
+#else
+    const unsigned sgv_shared = 0u;
+#endif
     // The warp's rays are t = warp, warp + 8, ...; what is per ray and not per bin (hand-off meta
     // word, angular bin) is looked up by one lane per ray, 32 rays at a time.
     for (int t0 = warp; t0 < pr.cnt; t0 += 32 * RTB_OWNER_WARPS) {
@@ -994,8 +1016,15 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, KS <= 2 ? RTB_OWNER_MINB
 #pragma unroll
             for (int q = 0; q < KS; q++)
                 Iv[q] = 0.0;
-            const int code = integrate_ray_ase_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, koff, Iv, KC,
-                                                        slab_addr);
+#ifdef RTB_OWNER_SEG_BASE
+            (void) slot;
+            const unsigned long long seg_ray =
+                (((unsigned long long) seg_hi << 32) | seg_lo) + (unsigned long long) ((unsigned) t * ray_bytes);
+            const SegRec *seg = reinterpret_cast<const SegRec *>(seg_ray);
+#else
+            const SegRec *seg = h.seg + slot * S;
+#endif
+            const int code = integrate_ray_ase_fast<KS>(P, s_gv, seg, meta, lane, koff, Iv, KC, slab_addr, sgv_shared);
             if (code != 0) {
                 if (lane == 0) {
                     const int ab = pr.ab0 + t * (int) P.n_parallel;

@@ -104,3 +104,29 @@ def test_tile_bounds_cover_everything():
                 assert 0 <= lo <= hi <= n and hi - lo <= per
                 seen += list(range(lo, hi))
             assert seen == list(range(n))
+
+
+def test_bench_workloads_scale_rows_with_the_gpu_count():
+    """bench.py --workload: every family keeps rays per GPU fixed under weak scaling (the image rows,
+    the sharded axis, are multiplied by the GPU count) and is the fixed image under strong scaling."""
+    import importlib
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    bench = importlib.import_module("bench")
+    saved = bench.WORKLOAD
+    try:
+        for kind, rays1 in (("ase_medium", 2994600), ("s4", 1596000), ("s4x", 1596000), ("spectral128", 1596000)):
+            bench.WORKLOAD = kind
+            p1, name1 = bench.workload(1, "weak")
+            p4, name4 = bench.workload(4, "weak")
+            ps, _ = bench.workload(4, "strong")
+            assert p1.n_rays == rays1 and p4.n_rays == 4 * rays1 and ps.n_rays == rays1, kind
+            assert p4.euv_beam.ny == 4 * p1.euv_beam.ny and p4.euv_beam.nx == p1.euv_beam.nx
+            assert "ny x4" in name4 and "ny x" not in name1
+        bench.WORKLOAD = "spectral128"
+        assert bench.workload(1, "weak")[0].euv_beam.nv == 128
+    finally:
+        bench.WORKLOAD = saved

@@ -102,11 +102,22 @@ def main():
             os.environ.pop("RTB200_OVERLAP", None)
         serial_ms, tm = staged_times(ctx_s, p, flags, torch)
         ctx_s.close()
+        # eikonal steps of the march (device counter; a counting instantiation of the kernel)
+        os.environ["RTB200_COUNT_STEPS"] = "1"
+        try:
+            ctx_c = lib.Context(0)
+        finally:
+            os.environ.pop("RTB200_COUNT_STEPS", None)
+        ctx_c.create_image(p, flags=flags)
+        march_steps = int(ctx_c.timings()["march_steps"])
+        ctx_c.close()
         W_seg = p.n_rays * (p.N - 1) * 3
         line = {"config": name, "baseline_config": cfg, "rays": p.n_rays, "N": p.N, "K": e.nv,
                 "gain_grid": [p.gain[1].Nx, p.gain[1].Ny], "ray_segments": W_seg,
                 "device_ms": dev_ms, "serialised_ms": serial_ms, "march_ms": tm["march_ms"],
                 "integrate_ms": tm["integrate_ms"],
+                "march_steps": march_steps, "march_steps_per_ray": march_steps / max(p.n_rays, 1),
+                "march_steps_per_s": march_steps / (tm["march_ms"] * 1e-3),
                 "e2e_ms": best_e2e * 1e3, "ray_segments_per_s_device": W_seg / (dev_ms * 1e-3),
                 "ray_segments_per_s_e2e": W_seg / best_e2e}
         per_upd = 32 if p.seed is None else 25  # FP64 instr per frequency update / per (ray, bin)
