@@ -437,7 +437,9 @@ int launch_pixels(rtb200_ctx *ctx, long long pix0, long long pix1, const Outputs
     if (rc)
         return rc;
     Handoff h{ ctx->d_seg.p, ctx->d_meta.p, need_exit ? ctx->d_exit.p : nullptr, nullptr, nullptr };
-    const bool owner = ctx->owner_ok && !out.Iv && !out.error;
+    // (the owner kernels address a pixel's records with 32-bit byte offsets: OwnerBase::ray)
+    const bool owner = ctx->owner_ok && !out.Iv && !out.error &&
+                       (long long) P.ab_max * std::max(S, 1) * (long long) sizeof(SegRec) < (1LL << 32);
     // Overlapped form (owner kernel): the march counts the closed ray slots of every pixel, the
     // integration is launched with programmatic stream serialization right behind it - nothing
     // between the two launches in the stream - and each of its CTAs waits for its pixel (and, when

@@ -637,13 +637,12 @@ struct PinnedConsts {
 #endif
 
 template <int KS>
-__device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const float *const *s_gv,
+__device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, unsigned sgv_shared,
                                                       const SegRec *seg, unsigned meta, int lane,
                                                       const int (&koff)[KS], double (&Iv)[KS],
-                                                      const PinnedConsts &KC, unsigned slab,
-                                                      unsigned sgv_shared = 0u)
+                                                      const PinnedConsts &KC, unsigned slab)
 {
-    (void) sgv_shared;
+    // sgv_shared: shared-space address of the CTA's table of lineshape base pointers ([N] x 64 bit)
     // slab: shared-space address of this warp's 32 x 16-byte record slab (opaque register)
     const int lo = meta & 0xfff, hi = (meta >> 12) & 0xfff;
     const int K = P.K;
@@ -665,7 +664,6 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
         bool nonzero = false;
         if (lane < cnt) {
             const int4 rv = RTB_HANDOFF_LD(reinterpret_cast<const int4 *>(&seg[c0 + lane]));
-#ifdef RTB_OWNER_SEG_BASE
             // (the table of lineshape base pointers through its shared-space address, kept opaque in
             // a uniform register: otherwise it is rebuilt from the CTA's shared window at every use)
             unsigned long long gvp;
@@ -673,9 +671,6 @@ __device__ __forceinline__ int integrate_ray_ase_fast(const DevProblem &P, const
                          : "=l"(gvp)
                          : "r"(sgv_shared + 8u * (unsigned) ((c0 + lane) / RTB_N_SUB + 1)));
             const float *row = reinterpret_cast<const float *>(gvp) + (size_t) rv.z * K;
-#else
-            const float *row = s_gv[(c0 + lane) / RTB_N_SUB + 1] + (size_t) rv.z * K;
-#endif
             const unsigned long long ra = reinterpret_cast<unsigned long long>(row);
             gvl_abs = (unsigned) rv.x & 0x7fffffffu;
             // gvl == 0 && evl == 0 (either sign of zero): gl = el = 0, the update is the identity
@@ -934,6 +929,30 @@ __device__ __forceinline__ void owner_wait_for_pixel(const Outputs &o, unsigned 
     __syncthreads();
 }
 
+// What the owner kernels address per ray, as uniform values that are built once per CTA: the
+// pixel's first hand-off record (a ray's records are then one 32-bit multiply-add away; left
+// alone, the 64-bit product slot * S is rebuilt from the kernel parameters for every ray) and the
+// shared-space address of the table of lineshape base pointers.
+struct OwnerBase {
+    unsigned seg_lo, seg_hi, ray_bytes, sgv_shared;
+    __device__ __forceinline__ OwnerBase(const SegRec *seg_pix, int S, const float *const *s_gv)
+    {
+        const unsigned long long a = reinterpret_cast<unsigned long long>(seg_pix);
+        seg_lo = uniform_u32((unsigned) a);
+        seg_hi = uniform_u32((unsigned) (a >> 32));
+        ray_bytes = (unsigned) S * (unsigned) sizeof(SegRec);
+        sgv_shared = uniform_u32((unsigned) __cvta_generic_to_shared(s_gv));
+    }
+    // records of the pixel's ray t (a pixel's records fit 32 bits of bytes: the host sizes chunks so
+    // that slots * S of a whole chunk stay below 2^31)
+    __device__ __forceinline__ const SegRec *ray(int t) const
+    {
+        const unsigned long long a =
+            (((unsigned long long) seg_hi << 32) | seg_lo) + (unsigned long long) ((unsigned) t * ray_bytes);
+        return reinterpret_cast<const SegRec *>(a);
+    }
+};
+
 #define RTB_OWNER_WARPS 8
 // Resident CTAs per SM the compiler budgets registers for: up to two lane slots (K <= 64) the
 // kernel fits 48 registers with a handful of spills outside the walk, and 40 warps per SM hide
@@ -979,16 +998,7 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, KS <= 2 ? RTB_OWNER_MINB
     }
     const PinnedConsts KC(P.kfp_g, exp_tab);
     const unsigned slab_addr = uniform_u32((unsigned) __cvta_generic_to_shared(&rec_slab[warp][0]));
-#ifdef RTB_OWNER_SEG_BASE
-    // The pixel's first hand-off record as a pair of uniform values: a ray's records are then one
-    // 32-bit multiply-add away (left alone, the 64-bit product slot * S is rebuilt for every ray).
-    const unsigned long long seg_pix = reinterpret_cast<unsigned long long>(h.seg + slot0 * S);
-    const unsigned seg_lo = uniform_u32((unsigned) seg_pix), seg_hi = uniform_u32((unsigned) (seg_pix >> 32));
-    const unsigned ray_bytes = (unsigned) S * (unsigned) sizeof(SegRec);
-    const unsigned sgv_shared = uniform_u32((unsigned) __cvta_generic_to_shared(s_gv));
-#else
-    const unsigned sgv_shared = 0u;
-#endif
+    const OwnerBase ob(h.seg + slot0 * S, S, s_gv);
     // The warp's rays are t = warp, warp + 8, ...; what is per ray and not per bin (hand-off meta
     // word, angular bin) is looked up by one lane per ray, 32 rays at a time.
     for (int t0 = warp; t0 < pr.cnt; t0 += 32 * RTB_OWNER_WARPS) {
@@ -1007,7 +1017,6 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, KS <= 2 ? RTB_OWNER_MINB
         const int n_here = min(32, (pr.cnt - t0 + RTB_OWNER_WARPS - 1) / RTB_OWNER_WARPS);
         for (int j = 0; j < n_here; j++) {
             const int t = t0 + j * RTB_OWNER_WARPS;
-            const long long slot = slot0 + t;
             const unsigned meta = uniform_from_lane(meta_l, lane, j);
             const int bin = (int) uniform_from_lane((unsigned) bin_l, lane, j);
             if (meta & RTB_META_INVALID)
@@ -1016,15 +1025,8 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, KS <= 2 ? RTB_OWNER_MINB
 #pragma unroll
             for (int q = 0; q < KS; q++)
                 Iv[q] = 0.0;
-#ifdef RTB_OWNER_SEG_BASE
-            (void) slot;
-            const unsigned long long seg_ray =
-                (((unsigned long long) seg_hi << 32) | seg_lo) + (unsigned long long) ((unsigned) t * ray_bytes);
-            const SegRec *seg = reinterpret_cast<const SegRec *>(seg_ray);
-#else
-            const SegRec *seg = h.seg + slot * S;
-#endif
-            const int code = integrate_ray_ase_fast<KS>(P, s_gv, seg, meta, lane, koff, Iv, KC, slab_addr, sgv_shared);
+            const int code = integrate_ray_ase_fast<KS>(P, ob.sgv_shared, ob.ray(t), meta, lane, koff, Iv, KC,
+                                                        slab_addr);
             if (code != 0) {
                 if (lane == 0) {
                     const int ab = pr.ab0 + t * (int) P.n_parallel;
@@ -1089,6 +1091,7 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, 3)
     const long long slot0 = (long long) blockIdx.x * P.ab_max;
     const PinnedConsts KC(P.kfp_g, exp_tab);
     const unsigned slab_addr = uniform_u32((unsigned) __cvta_generic_to_shared(&rec_slab[warp][0]));
+    const OwnerBase ob(h.seg + slot0 * S, S, s_gv);
     const int pi = __ldg(&P.pixI[pr.i]), pj = __ldg(&P.pixJ[pr.j]);
     const bool store = o.compact || (pi >= 0 && pj >= 0);
     const size_t opix = o.compact ? (size_t) (c.pix0 + blockIdx.x) : (size_t) pi + (size_t) pj * P.nx;
@@ -1119,7 +1122,6 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, 3)
             const int n_here = min(32, (pr.cnt - t0 + RTB_OWNER_WARPS - 1) / RTB_OWNER_WARPS);
             for (int j = 0; j < n_here; j++) {
                 const int t = t0 + j * RTB_OWNER_WARPS;
-                const long long slot = slot0 + t;
                 const unsigned meta = uniform_from_lane(meta_l, lane, j);
                 const int bin = (int) uniform_from_lane((unsigned) bin_l, lane, j);
                 if (meta & RTB_META_INVALID)
@@ -1128,7 +1130,7 @@ __global__ void __launch_bounds__(RTB_OWNER_WARPS * 32, 3)
 #pragma unroll
                 for (int q = 0; q < KS; q++)
                     Iv[q] = 0.0;
-                const int code = integrate_ray_ase_fast<KS>(P, s_gv, h.seg + slot * S, meta, lane, koff, Iv, KC,
+                const int code = integrate_ray_ase_fast<KS>(P, ob.sgv_shared, ob.ray(t), meta, lane, koff, Iv, KC,
                                                             slab_addr);
                 if (code != 0) {
                     if (lane == 0) {
